@@ -1,0 +1,497 @@
+#!/usr/bin/env python3
+"""Generate golden vectors for the hot path by running the UNMODIFIED reference.
+
+Runs only in the authoring container (needs /root/reference/code, which never
+travels to the GPU box).  Every fixture it writes under tests/golden/ is a small
+JSON file; inputs are re-derivable anywhere from `random.Random(seed)` (stdlib),
+outputs are stored as values (small cases) or sha256 digests (large cases).
+
+Digest convention: sha256 over the concatenation of
+little-endian u64 values; ExtensionFieldElement = c0,c1,c2 with trimmed
+coefficients zero-filled, elements in list order.
+
+Usage:  python tests/golden/make_golden.py <group> [...]
+Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs
+Heavy groups are meant to run in the background, one process each.
+"""
+import hashlib
+import json
+import os
+import pickle
+import random
+import struct
+import sys
+import time
+
+REF = os.environ.get("B2S_REFERENCE_DIR", "/root/reference/code")
+sys.path.insert(0, REF)
+sys.dont_write_bytecode = True
+
+from algebra import BaseField, BaseFieldElement  # noqa: E402
+from extension_field import ExtensionField, ExtensionFieldElement  # noqa: E402
+from univariate import Polynomial  # noqa: E402
+import ntt as ref_ntt  # noqa: E402
+from merkle import Merkle  # noqa: E402
+from ip import ProofStream  # noqa: E402
+from fri import Fri  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+P = 18446744069414584321
+field = BaseField.main()
+xfield = ExtensionField.main()
+XBF = xfield.modulus.coefficients[0].field  # canonical inner base field (SURVEY B5 rule 1)
+
+
+def dump(name, obj):
+    path = os.path.join(HERE, name)
+    with open(path, "w") as f:
+        json.dump(obj, f, indent=1, sort_keys=True)
+        f.write("\n")
+    print("wrote", path, flush=True)
+
+
+def bfe_digest(values):
+    return hashlib.sha256(b"".join(struct.pack("<Q", v.value) for v in values)).hexdigest()
+
+
+def xfe_triple(x):
+    c = [co.value for co in x.polynomial.coefficients]
+    return c + [0] * (3 - len(c))
+
+
+def xfe_digest(values):
+    h = hashlib.sha256()
+    for x in values:
+        h.update(struct.pack("<3Q", *xfe_triple(x)))
+    return h.hexdigest()
+
+
+def X(*coeffs):
+    """canonical-identity ExtensionFieldElement (SURVEY B5 rule 5)"""
+    return ExtensionFieldElement(Polynomial([BaseFieldElement(c, XBF) for c in coeffs]), xfield)
+
+
+def rand_bfe_list(seed, n):
+    R = random.Random(seed)
+    return [BaseFieldElement(R.randrange(P), field) for _ in range(n)]
+
+
+def rand_xfe_list(seed, n):
+    R = random.Random(seed)
+    return [X(R.randrange(P), R.randrange(P), R.randrange(P)) for _ in range(n)]
+
+
+# --------------------------------------------------------------------------
+def plain_ntt(vals, omega):
+    """iterative plain-int NTT used ONLY to build big FRI inputs (B5 rule 5);
+    validated below against the reference at small sizes before use."""
+    n = len(vals)
+    a = list(vals)
+    logn = n.bit_length() - 1
+    # bit reversal
+    j = 0
+    for i in range(1, n):
+        bit = n >> 1
+        while j & bit:
+            j ^= bit
+            bit >>= 1
+        j |= bit
+        if i < j:
+            a[i], a[j] = a[j], a[i]
+    length = 2
+    while length <= n:
+        w_len = pow(omega, n // length, P)
+        half = length // 2
+        tw = [1] * half
+        for i in range(1, half):
+            tw[i] = tw[i - 1] * w_len % P
+        for start in range(0, n, length):
+            for i in range(half):
+                u = a[start + i]
+                v = a[start + i + half] * tw[i] % P
+                a[start + i] = (u + v) % P
+                a[start + i + half] = (u - v) % P
+        length <<= 1
+    return a
+
+
+def fri_input(logn, expansion, seed):
+    """random degree < n/expansion XFE polynomial evaluated on the coset 7*omega^k
+    with the plain-int NTT, wrapped in canonical-identity objects."""
+    n = 1 << logn
+    R = random.Random(seed)
+    m = n // expansion
+    coeffs = [(R.randrange(P), R.randrange(P), R.randrange(P)) for _ in range(m)]
+    omega = field.primitive_nth_root(n).value
+    planes = []
+    for pl in range(3):
+        g = 1
+        col = []
+        for i in range(m):
+            col.append(coeffs[i][pl] * g % P)
+            g = g * 7 % P
+        col += [0] * (n - m)
+        planes.append(plain_ntt(col, omega))
+    cw = []
+    for i in range(n):
+        t = [planes[0][i], planes[1][i], planes[2][i]]
+        while t and t[-1] == 0:
+            t.pop()
+        cw.append(X(*t))
+    return coeffs, cw
+
+
+def run_fri(logn, expansion, s, seed, check_xevaluate=False):
+    n = 1 << logn
+    omega = field.primitive_nth_root(n)
+    fri = Fri(field.generator(), omega, n, expansion, s, xfield)
+    coeffs, cw = fri_input(logn, expansion, seed)
+    if check_xevaluate:
+        poly = Polynomial([X(*c) for c in coeffs])
+        ref_cw = fri.domain.xevaluate(poly, xfield)
+        assert xfe_digest(ref_cw) == xfe_digest(cw), "plain-int NTT disagrees with reference xevaluate"
+        assert pickle.dumps(ref_cw) == pickle.dumps(cw), "identity graph differs from reference objects"
+    ps = ProofStream()
+    t0 = time.time()
+    top = fri.prove(cw, ps)
+    dt = time.time() - t0
+    ser = ps.serialize()
+    root0 = Merkle(cw).root().hex() if logn <= 14 else None
+    out = {
+        "log_n": logn, "expansion": expansion, "num_colinearity_tests": s, "seed": seed,
+        "codeword_digest": xfe_digest(cw), "top_level_indices": top,
+        "transcript_len": len(ser), "transcript_sha256": hashlib.sha256(ser).hexdigest(),
+        "num_objects": len(ps.objects), "reference_seconds": round(dt, 3),
+        "round_roots": [o.hex() for o in ps.objects if isinstance(o, bytes)],
+        "root0": root0,
+    }
+    if logn <= 14:
+        v = fri.verify(ProofStream().deserialize(ser), Merkle(cw).root())
+        out["verify"] = bool(v)
+    return out
+
+
+# --------------------------------------------------------------------------
+def group_small():
+    g = {}
+    # GV1
+    w8 = field.primitive_nth_root(8)
+    v = [BaseFieldElement(i, field) for i in range(1, 9)]
+    g["gv1_ntt8"] = [x.value for x in ref_ntt.ntt(w8, v)]
+    g["gv1_intt8"] = [x.value for x in ref_ntt.intt(w8, ref_ntt.ntt(w8, v))]
+    # roots
+    g["roots"] = {str(k): field.primitive_nth_root(1 << k).value for k in range(1, 25)}
+    # BFE ntt/intt digests + full small outputs  (seed = log n)
+    g["ntt_bfe"] = {}
+    for logn in range(1, 15):
+        n = 1 << logn
+        w = field.primitive_nth_root(n)
+        x = rand_bfe_list(logn, n)
+        t0 = time.time()
+        y = ref_ntt.ntt(w, x)
+        dt = time.time() - t0
+        z = ref_ntt.intt(w, x)
+        e = {"ntt_digest": bfe_digest(y), "intt_digest": bfe_digest(z), "ntt_seconds": round(dt, 4)}
+        if logn <= 4:
+            e["ntt_values"] = [t.value for t in y]
+            e["intt_values"] = [t.value for t in z]
+        g["ntt_bfe"][str(logn)] = e
+        print("ntt_bfe", logn, dt, flush=True)
+    # XFE ntt digests (seed = 100 + log n)
+    g["ntt_xfe"] = {}
+    for logn in range(1, 13):
+        n = 1 << logn
+        w = xfield.lift(field.primitive_nth_root(n))
+        x = rand_xfe_list(100 + logn, n)
+        t0 = time.time()
+        y = ref_ntt.ntt(w, x)
+        dt = time.time() - t0
+        e = {"ntt_digest": xfe_digest(y), "ntt_seconds": round(dt, 4)}
+        if logn <= 10:
+            e["intt_digest"] = xfe_digest(ref_ntt.intt(w, x))
+        g["ntt_xfe"][str(logn)] = e
+        print("ntt_xfe", logn, dt, flush=True)
+    # coset evaluate / interpolate via Fri.Domain  (seed 300+, 400+)
+    g["coset"] = {}
+    for logn in (3, 6, 9, 11):
+        n = 1 << logn
+        w = field.primitive_nth_root(n)
+        dom = Fri.Domain(field.generator(), w, n)
+        for m in sorted({n // 4, n // 4 + 1, n}):
+            poly = Polynomial(rand_bfe_list(300 + logn, m))
+            ev = dom.evaluate(Polynomial(list(poly.coefficients)))
+            xpoly = Polynomial(rand_xfe_list(400 + logn, m))
+            xev = dom.xevaluate(xpoly, xfield)
+            e = {"evaluate_digest": bfe_digest(ev), "xevaluate_digest": xfe_digest(xev)}
+            if m == n:
+                ip = dom.interpolate(rand_bfe_list(500 + logn, n))
+                e["interpolate_digest"] = bfe_digest(ip.coefficients)
+                e["interpolate_len"] = len(ip.coefficients)
+                xip = dom.xinterpolate(rand_xfe_list(600 + logn, n))
+                e["xinterpolate_digest"] = xfe_digest(xip.coefficients)
+            g["coset"]["%d_%d" % (logn, m)] = e
+        print("coset", logn, flush=True)
+    # coset with a non-generator offset (test_ntt.py::test_coset_evaluate uses offset 2)
+    n = 512
+    w = field.primitive_nth_root(n)
+    poly = Polynomial(rand_bfe_list(777, 300))
+    two = BaseFieldElement(2, field)
+    g["coset_offset2"] = {"digest": bfe_digest(ref_ntt.fast_coset_evaluate(poly, two, w, n))}
+    # Polynomial.scale and evaluate_domain  (seed 700+)
+    R = random.Random(700)
+    poly = Polynomial(rand_bfe_list(701, 37))
+    fac = BaseFieldElement(R.randrange(P), field)
+    g["scale_bfe"] = {"factor": fac.value, "digest": bfe_digest(poly.scale(fac).coefficients)}
+    xpoly = Polynomial(rand_xfe_list(702, 29))
+    xfac = X(R.randrange(P), R.randrange(P), R.randrange(P))
+    g["scale_xfe"] = {"factor": xfe_triple(xfac), "digest": xfe_digest(xpoly.scale(xfac).coefficients)}
+    pts = rand_bfe_list(703, 50)
+    g["evaluate_domain_bfe"] = {"digest": bfe_digest(poly.evaluate_domain(pts))}
+    xpts = rand_xfe_list(704, 41)
+    g["evaluate_domain_xfe"] = {"digest": xfe_digest(xpoly.evaluate_domain(xpts))}
+    # structured: XFE poly on a base-field coset lifted into the extension field
+    w64 = xfield.lift(field.primitive_nth_root(64))
+    off = xfield.lift(field.generator())
+    cos = [off * (w64 ^ i) for i in range(64)]
+    xp64 = Polynomial(rand_xfe_list(705, 64))
+    g["evaluate_domain_xfe_coset64"] = {"digest": xfe_digest(xp64.evaluate_domain(cos))}
+    # XFE arithmetic known answers (seed 800)
+    R = random.Random(800)
+    cases = []
+    for _ in range(64):
+        a = X(R.randrange(P), R.randrange(P), R.randrange(P))
+        b = X(R.randrange(P), R.randrange(P), R.randrange(P))
+        cases.append({"a": xfe_triple(a), "b": xfe_triple(b), "mul": xfe_triple(a * b),
+                      "inv": xfe_triple(a.inverse()), "div": xfe_triple(a / b),
+                      "add": xfe_triple(a + b), "sub": xfe_triple(a - b)})
+    # degenerate shapes
+    for a, b in [(X(5), X(0, 0, 7)), (X(0, 3), X(0, 0, P - 1)), (X(P - 1, P - 1, P - 1), X(P - 1, P - 1, P - 1)),
+                 (X(1), X(2)), (X(0, 1), X(0, 1))]:
+        cases.append({"a": xfe_triple(a), "b": xfe_triple(b), "mul": xfe_triple(a * b),
+                      "inv": xfe_triple(a.inverse()), "div": xfe_triple(a / b),
+                      "add": xfe_triple(a + b), "sub": xfe_triple(a - b)})
+    g["xfe_arith"] = cases
+    # BFE arithmetic known answers (seed 801)
+    R = random.Random(801)
+    bc = []
+    specials = [0, 1, 2, P - 1, P - 2, (1 << 32) - 1, 1 << 32, (1 << 32) + 1, (1 << 63), P >> 1, 0xFFFFFFFF00000000]
+    pairs = [(a, b) for a in specials for b in specials] + [(R.randrange(P), R.randrange(P)) for _ in range(64)]
+    for a, b in pairs:
+        A, B = BaseFieldElement(a, field), BaseFieldElement(b, field)
+        bc.append([a, b, (A + B).value, (A - B).value, (A * B).value, A.inverse().value, (-A).value])
+    g["bfe_arith"] = bc
+    # xfield.sample known answers
+    R = random.Random(802)
+    sm = []
+    for _ in range(8):
+        seed = bytes(R.getrandbits(8) for _ in range(32))
+        sm.append({"seed": seed.hex(), "xfe": xfe_triple(xfield.sample(seed)), "bfe": field.sample(seed).value})
+    g["sample"] = sm
+    dump("small.json", g)
+
+    # ---- pickle leaf templates and Merkle ---------------------------------
+    m = {}
+    marks = [0xA1, 0xA2, 0xA3]
+    tpl = {}
+    for k in range(4):
+        tpl[str(k)] = pickle.dumps(X(*marks[:k])).hex()
+    m["xfe_marker_pickles"] = tpl
+    m["bfe_marker_pickle"] = pickle.dumps(BaseFieldElement(0xA1, field)).hex()
+    m["xfe_inner_bfe_marker_pickle"] = pickle.dumps(BaseFieldElement(0xA1, XBF)).hex()
+    # int encodings at boundaries
+    ints = [0, 1, 255, 256, 65535, 65536, (1 << 31) - 1, 1 << 31, (1 << 32) - 1, 1 << 32, (1 << 39) - 1, 1 << 39,
+            (1 << 40), (1 << 47) - 1, 1 << 47, (1 << 55) - 1, 1 << 55, (1 << 56), (1 << 63) - 1, 1 << 63, P - 1]
+    m["int_pickles"] = {str(v): pickle.dumps(v)[2:-1].hex() for v in ints}
+    # GV2
+    leaves = [X(1, 2, 3), X(P - 1, 0, 5), X(7), X()]
+    t = Merkle(leaves)
+    m["gv2"] = {"leaves": [xfe_triple(x) for x in leaves],
+                "preimage_lens": [len(pickle.dumps(x)) for x in leaves],
+                "root": t.root().hex(), "open2": [b.hex() for b in t.open(2)],
+                "nodes": [b.hex() for b in t.nodes]}
+    # random XFE / BFE codeword trees (seed 900+log n); boundary-sized ints mixed in
+    m["xfe_trees"] = {}
+    m["bfe_trees"] = {}
+    for logn in range(0, 11):
+        n = 1 << logn
+        R = random.Random(900 + logn)
+        vals = []
+        for i in range(n):
+            c = []
+            for _ in range(3):
+                r = R.random()
+                if r < 0.15:
+                    c.append(0)
+                elif r < 0.5:
+                    c.append(R.choice(ints))
+                else:
+                    c.append(R.randrange(P))
+            vals.append(c)
+        lv = []
+        for c in vals:
+            c = list(c)
+            while c and c[-1] == 0:
+                c.pop()
+            lv.append(X(*c))
+        t = Merkle(lv)
+        m["xfe_trees"][str(logn)] = {"root": t.root().hex(), "values": vals if logn <= 5 else None,
+                                     "nodes_sha256": hashlib.sha256(b"".join(t.nodes[1:])).hexdigest(),
+                                     "open_last": [b.hex() for b in t.open(n - 1)]}
+        bl = [BaseFieldElement(c[0], field) for c in vals]
+        tb = Merkle(bl)
+        m["bfe_trees"][str(logn)] = {"root": tb.root().hex(),
+                                     "nodes_sha256": hashlib.sha256(b"".join(tb.nodes[1:])).hexdigest()}
+    # uniform random XFE trees at the sizes GV-style (seed = 100+log n inputs)
+    m["xfe_trees_uniform"] = {}
+    for logn in (4, 8, 12, 14):
+        lv = rand_xfe_list(100 + logn, 1 << logn)
+        t = Merkle(lv)
+        m["xfe_trees_uniform"][str(logn)] = {"root": t.root().hex()}
+    # generic blobs (test_merkle.py style: lists of byte strings), non power of two counts
+    m["blob_trees"] = {}
+    for n in (1, 2, 3, 5, 8, 13, 64, 100):
+        R = random.Random(1000 + n)
+        lv = [[bytes(R.getrandbits(8) for _ in range(R.randrange(0, 256))),
+               bytes(R.getrandbits(8) for _ in range(R.randrange(0, 256)))] for _ in range(n)]
+        t = Merkle(lv)
+        m["blob_trees"][str(n)] = {"root": t.root().hex(), "depth": t.depth,
+                                   "open0": [b.hex() for b in t.open(0)],
+                                   "open_last": [b.hex() for b in t.open(n - 1)],
+                                   "nodes_sha256": hashlib.sha256(b"".join(t.nodes[1:])).hexdigest()}
+    dump("merkle.json", m)
+
+    # ---- FRI fold, sample_indices -----------------------------------------
+    f = {}
+    for logn in (4, 6, 8):
+        n = 1 << logn
+        R = random.Random(1100 + logn)
+        cw = rand_xfe_list(1100 + logn, n)
+        alpha = X(R.randrange(P), R.randrange(P), R.randrange(P))
+        omega = xfield.lift(field.primitive_nth_root(n))
+        offset = xfield.lift(field.generator())
+        one = xfield.one()
+        two = one + one
+        nxt = [two.inverse() * ((one + alpha / (offset * (omega ^ i))) * cw[i] +
+                                (one - alpha / (offset * (omega ^ i))) * cw[n // 2 + i]) for i in range(n // 2)]
+        f["fold_%d" % logn] = {"alpha": xfe_triple(alpha), "digest": xfe_digest(nxt),
+                               "values": [xfe_triple(x) for x in nxt] if logn == 4 else None}
+    fr = Fri(field.generator(), field.primitive_nth_root(1024), 1024, 16, 17, xfield)
+    R = random.Random(1200)
+    seed = bytes(R.getrandbits(8) for _ in range(32))
+    f["sample_indices"] = {"seed": seed.hex(), "size": 512, "reduced": 32, "number": 17,
+                           "indices": fr.sample_indices(seed, 512, 32, 17)}
+    dump("fold.json", f)
+
+
+def group_fri_small():
+    g = {"gv6": {}}
+    # validate the plain-int path against reference xevaluate + identity at 2^8
+    g["gv6"]["8"] = run_fri(8, 4, 8, 208, check_xevaluate=True)
+    for logn in (4, 5, 6, 10, 12, 14):
+        g["gv6"][str(logn)] = run_fri(logn, 4, min(8, 8), 200 + logn)
+        print("fri", logn, g["gv6"][str(logn)]["reference_seconds"], flush=True)
+    # expansion 32 / 40 checks (BASELINE config 4 as literally worded needs expansion >= 32)
+    g["exp32_s40_12"] = run_fri(12, 32, 40, 1312)
+    # test_fri.py configuration: degree 63, expansion 16, 17 checks, poly = [xfield(i)]
+    n = 1024
+    omega = field.primitive_nth_root(n)
+    fri = Fri(field.generator(), omega, n, 16, 17, xfield)
+    poly = Polynomial([xfield(i) for i in range(64)])
+    cw = fri.domain.xevaluate(poly)
+    ps = ProofStream()
+    top = fri.prove(cw, ps)
+    ser = ps.serialize()
+    g["test_fri"] = {"codeword_digest": xfe_digest(cw), "top_level_indices": top, "transcript_len": len(ser),
+                     "transcript_sha256": hashlib.sha256(ser).hexdigest(), "num_objects": len(ps.objects),
+                     "root0": Merkle(cw).root().hex()}
+    # GV3: 64 coeffs sampled from 30 random bytes, R = Random(5), n = 256
+    R = random.Random(5)
+    n = 256
+    fri = Fri(field.generator(), field.primitive_nth_root(n), n, 4, 8, xfield)
+    poly = Polynomial([xfield.sample(bytes(R.getrandbits(8) for _ in range(30))) for _ in range(64)])
+    cw = fri.domain.xevaluate(poly, xfield)
+    ps = ProofStream()
+    top = fri.prove(cw, ps)
+    ser = ps.serialize()
+    g["gv3"] = {"codeword_digest": xfe_digest(cw), "top_level_indices": top, "transcript_len": len(ser),
+                "transcript_sha256": hashlib.sha256(ser).hexdigest()}
+    dump("fri_small.json", g)
+
+
+def group_fri_big(logn):
+    r = run_fri(logn, 4, 8, 200 + logn)
+    dump("fri_%d.json" % logn, r)
+
+
+def group_ntt_big():
+    g = {}
+    for logn in (16, 18, 20):
+        n = 1 << logn
+        w = field.primitive_nth_root(n)
+        x = rand_bfe_list(logn, n)
+        t0 = time.time()
+        y = ref_ntt.ntt(w, x)
+        dt = time.time() - t0
+        g[str(logn)] = {"ntt_digest": bfe_digest(y), "ntt_seconds": round(dt, 2)}
+        print("ntt_big", logn, dt, flush=True)
+        if logn <= 18:
+            t0 = time.time()
+            z = ref_ntt.intt(w, x)
+            g[str(logn)]["intt_digest"] = bfe_digest(z)
+            g[str(logn)]["intt_seconds"] = round(time.time() - t0, 2)
+        dump("ntt_big.json", g)
+
+
+def group_xntt_big():
+    g = {}
+    for logn in (14, 16, 18):
+        n = 1 << logn
+        w = xfield.lift(field.primitive_nth_root(n))
+        x = rand_xfe_list(100 + logn, n)
+        t0 = time.time()
+        y = ref_ntt.ntt(w, x)
+        dt = time.time() - t0
+        g[str(logn)] = {"ntt_digest": xfe_digest(y), "ntt_seconds": round(dt, 2)}
+        print("xntt_big", logn, dt, flush=True)
+        dump("xntt_big.json", g)
+
+
+def group_bfs():
+    """GV7: BrainfuckStark.prove('++++') with seeded urandom."""
+    R = random.Random(1234)
+    fake = lambda n: bytes(R.getrandbits(8) for _ in range(n))  # noqa: E731
+    os.urandom = fake
+    import salted_merkle
+    salted_merkle.urandom = fake
+    from vm import VirtualMachine
+    from brainfuck_stark import BrainfuckStark
+    program = VirtualMachine.compile("++++")
+    running_time, input_symbols, output_symbols = VirtualMachine.run(program)
+    processor_matrix, memory_matrix, instruction_matrix, input_matrix, output_matrix = VirtualMachine.simulate(
+        program, input_data=input_symbols)
+    bfs = BrainfuckStark(running_time, len(memory_matrix), program, input_symbols, output_symbols)
+    t0 = time.time()
+    proof = bfs.prove(program, processor_matrix, memory_matrix, instruction_matrix, input_matrix, output_matrix)
+    dt = time.time() - t0
+    ok = bfs.verify(proof)
+    dump("bfs.json", {"program": "++++", "urandom_seed": 1234, "proof_len": len(proof),
+                      "proof_sha256": hashlib.sha256(proof).hexdigest(), "verify": bool(ok),
+                      "fri_domain_length": bfs.fri.domain.length, "prove_seconds": round(dt, 1)})
+
+
+if __name__ == "__main__":
+    for grp in sys.argv[1:]:
+        if grp == "small":
+            group_small()
+        elif grp == "fri_small":
+            group_fri_small()
+        elif grp.startswith("fri_"):
+            group_fri_big(int(grp[4:]))
+        elif grp == "ntt_big":
+            group_ntt_big()
+        elif grp == "xntt_big":
+            group_xntt_big()
+        elif grp == "bfs":
+            group_bfs()
+        else:
+            raise SystemExit("unknown group " + grp)
