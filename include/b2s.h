@@ -1,0 +1,158 @@
+/*
+ * b2s.h -- C ABI of libb2s.so, the sm_100a polynomial / FRI / Merkle engine that sits
+ * behind the call surface of aszepieniec/stark-brainfuck's hot path.
+ *
+ * The reference has no FFI layer (it is pure Python); each entry point below names the
+ * reference function it replaces (paths relative to the reference checkout).  The
+ * reference-side binding is a ctypes stub, shown in INTEGRATION.md and implemented in
+ * stark_brainfuck_b200/_lib.py.
+ *
+ * Conventions
+ *  - Field elements are canonical uint64 values in [0, p), p = 2^64 - 2^32 + 1
+ *    (code/algebra.py:110-115).  Montgomery or lazy forms never cross this boundary.
+ *  - An extension-field vector (code/extension_field.py, F_p[X]/(X^3 - X + 1)) is three
+ *    planes c0, c1, c2 of n uint64 each; trimmed (absent) coefficients are zero.
+ *  - `d_` pointers are DEVICE pointers owned by the caller (in the Python glue: torch
+ *    uint8/int64 tensors used as byte buffers).  `h_` pointers are HOST pointers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer
+ *    entry points only enqueue work; they do not synchronise.  `_host` entry points copy
+ *    in, run, copy out and synchronise before returning.
+ *  - Every function returns 0 on success or a negative B2S_ERR_* code and never throws;
+ *    b2s_last_error() returns a thread-local message for the last failure.
+ *  - Precondition failures that the reference reports with `assert` come back as
+ *    B2S_ERR_ASSERT_*; the glue turns them into AssertionError.
+ */
+#ifndef B2S_H
+#define B2S_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_OK 0
+#define B2S_ERR_CUDA (-1)
+#define B2S_ERR_ARG (-2)
+#define B2S_ERR_NOMEM (-3)
+#define B2S_ERR_NCCL (-4)
+#define B2S_ERR_ASSERT_NPO2 (-10)      /* code/ntt.py:5-6   "cannot compute ntt of non-power-of-two sequence" */
+#define B2S_ERR_ASSERT_ROOT (-11)      /* code/ntt.py:13-14 "primitive root must be nth root of unity" */
+#define B2S_ERR_ASSERT_PRIMITIVE (-12) /* code/ntt.py:15-16 "primitive root is not primitive nth root of unity" */
+
+#define B2S_TPL_MAX_BYTES 2048
+
+/* Byte templates of pickle.dumps(leaf) for field-element Merkle leaves
+ * (code/merkle.py:29-32 hashes pickle.dumps(leaf)).  The glue derives them at start-up
+ * by pickling marker elements of the caller's own classes, so module names, memo
+ * indices and the shared-`field` identity pattern are whatever the caller's objects
+ * produce.  Template k is used for an element with k coefficients; its k+1 byte
+ * segments are interleaved with the k pickled integers:
+ *     PROTO 4 | FRAME(len) | seg0 INT(c0) seg1 INT(c1) ... seg_k          (seg_k ends in STOP)
+ */
+typedef struct b2s_leaf_templates {
+    uint32_t n_slots;       /* 1: BaseFieldElement leaves; 3: ExtensionFieldElement leaves */
+    uint32_t trim;          /* 1: k = number of coefficients left after trimming trailing zeros
+                               (code/extension_field.py:6-9); 0: k = n_slots always */
+    uint32_t seg_off[4][5]; /* template k, segment j = bytes[seg_off[k][j] .. seg_off[k][j+1]) */
+    uint8_t bytes[B2S_TPL_MAX_BYTES];
+} b2s_leaf_templates;
+
+/* ---- library / device management -------------------------------------------------- */
+int b2s_version(void);
+const char *b2s_last_error(void);
+/* Select the CUDA device for the calling thread and create the per-device caches.
+ * Fails (B2S_ERR_CUDA) when no sm_100 device is visible: there is no CPU fallback. */
+int b2s_init(int device);
+int b2s_shutdown(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t b2s_launch_count(void);
+int b2s_device_sm_count(void);
+
+/* ---- scalar helpers (host side, exact) -------------------------------------------- */
+/* code/algebra.py:89-108, :39-46 */
+uint64_t b2s_gl_mul(uint64_t a, uint64_t b);
+uint64_t b2s_gl_pow(uint64_t a, uint64_t e);
+uint64_t b2s_gl_inv(uint64_t a);
+
+/* ---- NTT family --------------------------------------------------------------------
+ * One entry point covers code/ntt.py:4-23 (ntt), :26-42 (intt), :164-168
+ * (fast_coset_evaluate), :171-174 (fast_coset_interpolate), code/fri.py:26-44
+ * (Fri.Domain.evaluate/xevaluate/interpolate/xinterpolate) and the scale step of
+ * code/univariate.py:168-169 that those wrappers fuse.
+ *
+ *   inverse == 0:  out[k] = sum_{j < n_in} (offset^j * in[j]) * omega^(j*k),  k < n = 2^log_n
+ *                  (coefficients beyond n_in are the zero padding of code/fri.py:28-29)
+ *   inverse != 0:  out[j] = offset^(-j) * n^(-1) * sum_k in[k] * omega^(-j*k)     (n_in == n)
+ *
+ * offset == 1 gives the plain ntt / intt.  Natural order in and out.  `n_planes`
+ * independent vectors (1 for a base-field vector, 3 for an extension-field vector, any
+ * number for a batch of columns) are transformed in one call; plane q starts at
+ * d_in + q*in_stride and d_out + q*out_stride (strides in elements).  d_in == d_out is
+ * allowed when in_stride == out_stride.  Scratch comes from the stream-ordered pool.
+ * Checks the asserts of code/ntt.py:13-16 on omega (B2S_ERR_ASSERT_*). */
+int b2s_ntt(const uint64_t *d_in, uint64_t in_stride, uint32_t n_in, uint64_t *d_out, uint64_t out_stride,
+            uint32_t log_n, uint32_t n_planes, uint64_t omega, uint64_t offset, int inverse, void *stream);
+/* Same through host buffers: H2D, transform, D2H, synchronise (the e2e path). */
+int b2s_ntt_host(const uint64_t *h_in, uint64_t in_stride, uint32_t n_in, uint64_t *h_out, uint64_t out_stride,
+                 uint32_t log_n, uint32_t n_planes, uint64_t omega, uint64_t offset, int inverse);
+
+/* code/univariate.py:168-169 Polynomial.scale: out[i] = factor^i * in[i].
+ * n_planes == 1: base-field coefficients, factor[0] used.  n_planes == 3: extension-field
+ * coefficients with an extension-field factor (factor[0..2]). */
+int b2s_scale(const uint64_t *d_in, uint64_t in_stride, uint64_t *d_out, uint64_t out_stride, uint64_t n,
+              uint32_t n_planes, const uint64_t factor[3], void *stream);
+
+/* code/univariate.py:145-154 Polynomial.evaluate_domain on ARBITRARY points (running-power
+ * evaluation per point).  coeff_planes / point_planes are 1 or 3; the output has
+ * max(coeff_planes, point_planes) planes.  (Points that form a coset offset*omega^k are
+ * routed to b2s_ntt by the glue instead.) */
+int b2s_eval_points(const uint64_t *d_coeffs, uint64_t coeff_stride, uint32_t coeff_planes, uint64_t n_coeffs,
+                    const uint64_t *d_points, uint64_t point_stride, uint32_t point_planes, uint64_t n_points,
+                    uint64_t *d_out, uint64_t out_stride, void *stream);
+
+/* ---- Merkle ------------------------------------------------------------------------
+ * code/merkle.py:8-41: BLAKE2b-512 tree, heap layout.  d_nodes holds 2*n slots of 64
+ * bytes: slot n+i = blake2b(pickle.dumps(leaf_i)), slot k = blake2b(slot 2k | slot 2k+1),
+ * slot 1 = root, slot 0 unused (zeroed).  Leaves are field elements given as planes
+ * (n_slots planes of n values, n a power of two); their pickle preimages are emitted on
+ * the device from `tpl`. */
+int b2s_merkle_field(const uint64_t *d_planes, uint64_t plane_stride, uint64_t n, const b2s_leaf_templates *tpl,
+                     uint8_t *d_nodes, void *stream);
+/* Arbitrary picklable leaves (code/test_merkle.py:57-61): the caller pickles on the host;
+ * leaf i is d_bytes[d_offsets[i] .. d_offsets[i+1]).  n_leafs need not be a power of two:
+ * unused leaf slots behave as the reference's 32-byte zero placeholders
+ * (code/merkle.py:26).  d_nodes holds 2*npo2 slots. */
+int b2s_merkle_blobs(const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_leafs, uint64_t npo2,
+                     uint8_t *d_nodes, void *stream);
+/* code/merkle.py:46-52 open(): copies the `depth` sibling digests of each index, leaf
+ * level first, to host memory: h_paths[q*depth*64 ...].  Synchronises. */
+int b2s_merkle_open(const uint8_t *d_nodes, uint64_t npo2, const uint64_t *h_indices, uint32_t n_indices,
+                    uint8_t *h_paths, void *stream);
+
+/* ---- FRI ---------------------------------------------------------------------------
+ * One commit round of code/fri.py:91-139 on an extension-field codeword of N values:
+ *   d_next[i] = 2^-1 * ((1 + alpha/(offset*omega^i)) * cw[i] + (1 - alpha/(offset*omega^i)) * cw[N/2+i])
+ * for i < N/2 (code/fri.py:127-128).  If d_next_nodes != NULL the Merkle tree of the
+ * folded codeword (code/fri.py:108 of the NEXT round) is built in the same call
+ * (leaf hashing fused with the fold). */
+int b2s_fri_fold(const uint64_t *d_cw, uint64_t cw_stride, uint64_t N, const uint64_t alpha[3], uint64_t offset,
+                 uint64_t omega, uint64_t *d_next, uint64_t next_stride, const b2s_leaf_templates *tpl,
+                 uint8_t *d_next_nodes, void *stream);
+/* Gather elements of planes at the given indices to the host (code/fri.py:150, :169 read
+ * tree.leafs[i] / last_codeword[i]): h_out[q*n_planes + plane].  Synchronises. */
+int b2s_gather(const uint64_t *d_planes, uint64_t plane_stride, uint32_t n_planes, const uint64_t *h_indices,
+               uint32_t n_indices, uint64_t *h_out, void *stream);
+
+/* ---- timing helper -----------------------------------------------------------------
+ * Runs b2s_ntt `iters` times back to back on `stream` bracketed by CUDA events and
+ * returns the mean milliseconds per call in *ms (used by bench.py for the roofline of the
+ * dominant kernel; torch.cuda.Event only sees torch's current stream). */
+int b2s_ntt_timed(const uint64_t *d_in, uint64_t in_stride, uint32_t n_in, uint64_t *d_out, uint64_t out_stride,
+                  uint32_t log_n, uint32_t n_planes, uint64_t omega, uint64_t offset, int inverse, void *stream,
+                  uint32_t iters, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H */

@@ -1,0 +1,111 @@
+// capi.cu -- library management, error reporting and the NTT entry points of include/b2s.h
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.h"
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+static int g_sm_count = 0;
+
+void b2s_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" int b2s_version(void) { return 1; }
+extern "C" const char *b2s_last_error(void) { return g_err; }
+extern "C" uint64_t b2s_launch_count(void) { return g_launches.load(); }
+extern "C" int b2s_device_sm_count(void) { return g_sm_count; }
+
+extern "C" uint64_t b2s_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a % GL_P, b % GL_P); }
+extern "C" uint64_t b2s_gl_pow(uint64_t a, uint64_t e) { return gl_pow(a % GL_P, e); }
+extern "C" uint64_t b2s_gl_inv(uint64_t a) { return gl_inv(a % GL_P); }
+
+extern "C" int b2s_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        b2s_set_error("no CUDA device visible (%s); libb2s has no CPU fallback",
+                      e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return B2S_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        b2s_set_error("device %d out of range (%d visible)", device, count);
+        return B2S_ERR_ARG;
+    }
+    B2S_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2S_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        b2s_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return B2S_ERR_CUDA;
+    }
+    g_sm_count = prop.multiProcessorCount;
+    // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+    cudaMemPool_t pool;
+    B2S_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = UINT64_MAX;
+    B2S_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    return 0;
+}
+
+extern "C" int b2s_shutdown(void) {
+    cudaDeviceSynchronize();
+    ntt_cache_clear();
+    return 0;
+}
+
+extern "C" int b2s_ntt(const uint64_t *d_in, uint64_t in_stride, uint32_t n_in, uint64_t *d_out, uint64_t out_stride,
+                       uint32_t log_n, uint32_t n_planes, uint64_t omega, uint64_t offset, int inverse, void *stream) {
+    return ntt_run(d_in, in_stride, n_in, d_out, out_stride, log_n, n_planes, omega, offset, inverse,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int b2s_ntt_host(const uint64_t *h_in, uint64_t in_stride, uint32_t n_in, uint64_t *h_out,
+                            uint64_t out_stride, uint32_t log_n, uint32_t n_planes, uint64_t omega, uint64_t offset,
+                            int inverse) {
+    if (log_n > 30) {
+        b2s_set_error("log_n %u too large", log_n);
+        return B2S_ERR_ARG;
+    }
+    const u64 n = (u64)1 << log_n;
+    cudaStream_t st = 0;
+    u64 *d_in = nullptr, *d_out = nullptr;
+    B2S_CUDA(cudaMallocAsync(&d_in, sizeof(u64) * (n_in ? n_in : 1) * n_planes, st));
+    B2S_CUDA(cudaMallocAsync(&d_out, sizeof(u64) * n * n_planes, st));
+    if (n_in)
+        B2S_CUDA(cudaMemcpy2DAsync(d_in, sizeof(u64) * n_in, h_in, sizeof(u64) * in_stride, sizeof(u64) * n_in, n_planes,
+                                   cudaMemcpyHostToDevice, st));
+    int rc = ntt_run(d_in, n_in, n_in, d_out, n, log_n, n_planes, omega, offset, inverse, st);
+    if (rc == 0)
+        B2S_CUDA(cudaMemcpy2DAsync(h_out, sizeof(u64) * out_stride, d_out, sizeof(u64) * n, sizeof(u64) * n, n_planes,
+                                   cudaMemcpyDeviceToHost, st));
+    cudaFreeAsync(d_in, st);
+    cudaFreeAsync(d_out, st);
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}
+
+extern "C" int b2s_ntt_timed(const uint64_t *d_in, uint64_t in_stride, uint32_t n_in, uint64_t *d_out,
+                             uint64_t out_stride, uint32_t log_n, uint32_t n_planes, uint64_t omega, uint64_t offset,
+                             int inverse, void *stream, uint32_t iters, float *ms) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    B2S_CUDA(cudaEventCreate(&e0));
+    B2S_CUDA(cudaEventCreate(&e1));
+    B2S_CUDA(cudaEventRecord(e0, st));
+    int rc = 0;
+    for (uint32_t i = 0; i < iters && rc == 0; ++i)
+        rc = ntt_run(d_in, in_stride, n_in, d_out, out_stride, log_n, n_planes, omega, offset, inverse, st);
+    B2S_CUDA(cudaEventRecord(e1, st));
+    B2S_CUDA(cudaEventSynchronize(e1));
+    float t = 0;
+    B2S_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ms) *ms = iters ? t / iters : 0.f;
+    return rc;
+}

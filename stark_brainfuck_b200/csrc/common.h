@@ -1,0 +1,46 @@
+// common.h -- internal declarations shared by the translation units of libb2s.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/b2s.h"
+#include "gl64.cuh"
+
+extern std::atomic<uint64_t> g_launches;
+void b2s_set_error(const char *fmt, ...);
+
+#define B2S_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            b2s_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+            return e_ == cudaErrorMemoryAllocation ? B2S_ERR_NOMEM : B2S_ERR_CUDA;                \
+        }                                                                                         \
+    } while (0)
+
+// count + check a kernel launch
+#define B2S_LAUNCHED()                                                                            \
+    do {                                                                                          \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
+        B2S_CUDA(cudaGetLastError());                                                             \
+    } while (0)
+
+static inline uint32_t ilog2_u64(uint64_t v) {
+    uint32_t r = 0;
+    while (v >>= 1) ++r;
+    return r;
+}
+
+// ---- internal device-side entry points used across files -------------------------------
+// ntt.cu
+int ntt_run(const u64 *d_in, u64 in_stride, u32 n_in, u64 *d_out, u64 out_stride, u32 log_n, u32 n_planes, u64 omega,
+            u64 offset, int inverse, cudaStream_t st);
+void ntt_cache_clear();
+// merkle.cu
+int merkle_field_run(const u64 *d_planes, u64 stride, u64 n, const b2s_leaf_templates *tpl, u8 *d_nodes,
+                     cudaStream_t st);
+int merkle_upper_run(u8 *d_nodes, u64 npo2, cudaStream_t st);
+int merkle_upload_templates(const b2s_leaf_templates *tpl, cudaStream_t st);

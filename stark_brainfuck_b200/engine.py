@@ -1,0 +1,204 @@
+"""Array-level host API over the C ABI: device-resident planes in, device-resident planes out.
+
+torch is used only for device memory (int64 / uint8 tensors as byte buffers) and streams;
+all arithmetic happens inside libb2s.so.  Shapes: a base-field vector is (1, n) int64, an
+extension-field vector (3, n) int64 (planes c0, c1, c2), a batch of columns (q, n).  The
+int64 dtype is a container for uint64 bit patterns.
+
+`Engine(lib=..., device=...)` exists so that tests/ can inject a host-memory backend with
+the same C ABI; the default constructor loads libb2s.so, initialises the CUDA device and
+raises if either is missing -- there is no CPU fallback in the product path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+P = 18446744069414584321
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device_index=0, lib=None, device=None):
+        if lib is None:
+            if not torch.cuda.is_available():
+                raise _lib.B2SError("no CUDA device: stark_brainfuck_b200 has no CPU fallback")
+            lib = _lib.load()
+            torch.cuda.set_device(device_index)
+            _lib.check(lib, lib.b2s_init(device_index))
+            device = torch.device("cuda", device_index)
+        self.lib = lib
+        self.device = torch.device(device)
+        self.templates = {}  # name -> LeafTemplates
+
+    # ---- plumbing ----------------------------------------------------------------
+    def stream_ptr(self):
+        if self.device.type == "cuda":
+            return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(0)
+
+    def upload(self, arr, pinned=False):
+        """numpy uint64 array (n,) or (q, n) -> device int64 tensor (q, n)"""
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        t = torch.from_numpy(a.view(np.int64))
+        if self.device.type == "cuda":
+            if pinned:
+                t = t.pin_memory()
+            return t.to(self.device, non_blocking=pinned)
+        return t.clone()
+
+    def download(self, t):
+        """device tensor -> numpy uint64 array with the same shape (synchronises)"""
+        return t.detach().cpu().contiguous().numpy().view(np.uint64)
+
+    def empty(self, planes, n):
+        return torch.empty((planes, n), dtype=torch.int64, device=self.device)
+
+    def check(self, rc):
+        _lib.check(self.lib, rc)
+
+    def launch_count(self):
+        return int(self.lib.b2s_launch_count())
+
+    # ---- NTT family ---------------------------------------------------------------
+    def ntt(self, x, log_n, omega, offset=1, inverse=False, out=None):
+        """code/ntt.py:4-42, :164-174 on planes.  x: (q, n_in) with n_in <= 2^log_n
+        (forward: missing coefficients are zero padding; inverse: n_in == n)."""
+        q, n_in = x.shape
+        n = 1 << log_n
+        assert x.dtype == torch.int64 and x.stride(1) == 1
+        if out is None:
+            out = self.empty(q, n)
+        self.check(self.lib.b2s_ntt(_ptr(x), x.stride(0) if q > 1 else max(n_in, 1), n_in, _ptr(out),
+                                    out.stride(0) if q > 1 else n, log_n, q, omega, offset, 1 if inverse else 0,
+                                    self.stream_ptr()))
+        return out
+
+    def ntt_host(self, h_in, log_n, omega, offset=1, inverse=False, h_out=None):
+        """same through host buffers (pinned int64 CPU tensors): H2D + kernels + D2H"""
+        q, n_in = h_in.shape
+        n = 1 << log_n
+        if h_out is None:
+            h_out = torch.empty((q, n), dtype=torch.int64, pin_memory=self.device.type == "cuda")
+        self.check(self.lib.b2s_ntt_host(_ptr(h_in), h_in.stride(0), n_in, _ptr(h_out), h_out.stride(0), log_n, q,
+                                         omega, offset, 1 if inverse else 0))
+        return h_out
+
+    def ntt_timed(self, x, log_n, omega, offset=1, inverse=False, out=None, iters=10):
+        q, n_in = x.shape
+        n = 1 << log_n
+        if out is None:
+            out = self.empty(q, n)
+        ms = C.c_float(0)
+        self.check(self.lib.b2s_ntt_timed(_ptr(x), x.stride(0) if q > 1 else max(n_in, 1), n_in, _ptr(out),
+                                          out.stride(0) if q > 1 else n, log_n, q, omega, offset,
+                                          1 if inverse else 0, self.stream_ptr(), iters, C.byref(ms)))
+        return ms.value, out
+
+    def scale(self, x, factor):
+        """code/univariate.py:168-169.  factor: int (base field) or 3 ints (extension field)"""
+        q, n = x.shape
+        f = (C.c_uint64 * 3)(*([factor, 0, 0] if isinstance(factor, int) else list(factor)))
+        out = torch.empty_like(x)
+        self.check(self.lib.b2s_scale(_ptr(x), x.stride(0), _ptr(out), out.stride(0), n, q, f, self.stream_ptr()))
+        return out
+
+    def eval_points(self, coeffs, points):
+        """code/univariate.py:145-154 on arbitrary points"""
+        cq, m = coeffs.shape
+        pq, k = points.shape
+        out = self.empty(max(cq, pq), k)
+        self.check(self.lib.b2s_eval_points(_ptr(coeffs), coeffs.stride(0), cq, m, _ptr(points), points.stride(0), pq,
+                                            k, _ptr(out), out.stride(0), self.stream_ptr()))
+        return out
+
+    # ---- Merkle -------------------------------------------------------------------
+    def merkle_field(self, planes, tpl):
+        """code/merkle.py:8-41 over field-element leaves; returns nodes (2n, 64) uint8"""
+        q, n = planes.shape
+        assert q == tpl.n_slots
+        nodes = torch.empty((2 * n, 64), dtype=torch.uint8, device=self.device)
+        self.check(self.lib.b2s_merkle_field(_ptr(planes), planes.stride(0), n, C.byref(tpl), _ptr(nodes),
+                                             self.stream_ptr()))
+        return nodes
+
+    def merkle_blobs(self, blobs):
+        """arbitrary leaves already pickled by the caller (code/test_merkle.py:57-61)"""
+        n = len(blobs)
+        npo2 = 1
+        while npo2 < n:
+            npo2 *= 2
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(b) for b in blobs])
+        data = np.frombuffer(b"".join(blobs) + b"\0" * 8, dtype=np.uint8)
+        d_data = torch.from_numpy(data.copy()).to(self.device)
+        d_offs = self.upload(offs)
+        nodes = torch.empty((2 * npo2, 64), dtype=torch.uint8, device=self.device)
+        self.check(self.lib.b2s_merkle_blobs(_ptr(d_data), _ptr(d_offs), n, npo2, _ptr(nodes), self.stream_ptr()))
+        return nodes
+
+    def merkle_open(self, nodes, indices):
+        """code/merkle.py:46-52 for several indices: list of lists of 64-byte digests"""
+        npo2 = nodes.shape[0] // 2
+        depth = npo2.bit_length() - 1
+        if depth == 0 or not indices:
+            return [[] for _ in indices]
+        idx = np.asarray(indices, dtype=np.uint64)
+        out = np.empty((len(indices), depth, 64), dtype=np.uint8)
+        self.check(self.lib.b2s_merkle_open(_ptr(nodes), npo2, idx.ctypes.data_as(C.c_void_p), len(indices),
+                                            out.ctypes.data_as(C.c_void_p), self.stream_ptr()))
+        return [[out[q, j].tobytes() for j in range(depth)] for q in range(len(indices))]
+
+    def root(self, nodes):
+        return bytes(self.download_bytes(nodes[1]))
+
+    def download_bytes(self, t):
+        return t.detach().cpu().contiguous().numpy().tobytes()
+
+    # ---- FRI ----------------------------------------------------------------------
+    def fri_fold(self, cw, alpha, offset, omega, tpl=None):
+        """code/fri.py:127-128 (+ Merkle tree of the folded codeword when tpl is given)"""
+        q, N = cw.shape
+        assert q == 3
+        nxt = self.empty(3, N // 2)
+        nodes = torch.empty((N, 64), dtype=torch.uint8, device=self.device) if tpl is not None else None
+        a = (C.c_uint64 * 3)(*[int(v) for v in alpha])
+        self.check(self.lib.b2s_fri_fold(_ptr(cw), cw.stride(0), N, a, offset, omega, _ptr(nxt), nxt.stride(0),
+                                         C.byref(tpl) if tpl is not None else None,
+                                         _ptr(nodes) if nodes is not None else None, self.stream_ptr()))
+        return nxt, nodes
+
+    def gather(self, planes, indices):
+        """planes[:, indices] to the host as numpy (len(indices), q) uint64"""
+        q, n = planes.shape
+        if not len(indices):
+            return np.empty((0, q), dtype=np.uint64)
+        idx = np.asarray(indices, dtype=np.uint64)
+        out = np.empty((len(indices), q), dtype=np.uint64)
+        self.check(self.lib.b2s_gather(_ptr(planes), planes.stride(0), q, idx.ctypes.data_as(C.c_void_p), len(indices),
+                                       out.ctypes.data_as(C.c_void_p), self.stream_ptr()))
+        return out
+
+
+_default = None
+
+
+def default_engine():
+    """process-wide engine on cuda:LOCAL_RANK (created on first use; raises without CUDA)"""
+    global _default
+    if _default is None:
+        import os
+        _default = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default
+
+
+def set_default_engine(e):
+    global _default
+    _default = e

@@ -1,0 +1,502 @@
+"""Object-level host glue: the reference's call surface implemented on the engine.
+
+One `Glue` serves both front ends:
+  * dropin.py patches these functions into the real reference modules
+    (ntt.ntt/intt/fast_coset_*, Polynomial.scale/evaluate_domain, Fri.Domain.*,
+    Fri.commit/query/query_last/prove, Merkle) so brainfuck_stark.prove() runs unmodified;
+  * mirror/ (the standalone host-side mirror of that interface) calls them directly.
+
+Argument meaning, return types, error behaviour (AssertionError / IndexError) and the
+object identity graph that pickle observes follow the reference; see the per-function
+citations.  All heavy arithmetic happens in libb2s.so through `Engine`.
+"""
+import pickle
+
+import numpy as np
+
+from .engine import P, default_engine
+
+
+def _ilog2(n):
+    return n.bit_length() - 1
+
+
+class Glue:
+    def __init__(self, binding, engine=None):
+        self.B = binding
+        self._engine = engine
+        self._xtpl = {}  # id(xfield) -> (xfield, templates)
+        self._btpl = {}  # id(field)  -> (field, templates)
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = default_engine()
+        return self._engine
+
+    # ------------------------------------------------------------------ helpers
+    def base_value(self, e, what="element"):
+        """int value of a BaseFieldElement or of a lifted ExtensionFieldElement (code/fri.py:37)"""
+        if self.B.is_bfe(e):
+            return e.value
+        if self.B.is_xfe(e):
+            co = e.polynomial.coefficients
+            if len(co) == 0:
+                return 0
+            if len(co) == 1:
+                return co[0].value
+            return None
+        raise TypeError("%s must be a field element, got %r" % (what, type(e)))
+
+    def xfe_templates(self, xfield):
+        ent = self._xtpl.get(id(xfield))
+        if ent is None or ent[0] is not xfield:
+            ent = (xfield, self.B.xfe_templates(xfield))
+            self._xtpl[id(xfield)] = ent
+        return ent[1]
+
+    def bfe_templates(self, field):
+        ent = self._btpl.get(id(field))
+        if ent is None or ent[0] is not field:
+            ent = (field, self.B.bfe_templates(field))
+            self._btpl[id(field)] = ent
+        return ent[1]
+
+    def _to_device(self, values):
+        """list of field elements -> (device planes, kind, field object for the results)"""
+        first = values[0]
+        if self.B.is_xfe(first):
+            return self.engine.upload(self.B.xfe_to_np(values)), "x", first.field
+        if self.B.is_bfe(first):
+            return self.engine.upload(self.B.bfe_to_np(values)), "b", first.field
+        raise TypeError("cannot transform a list of %r" % type(first))
+
+    def _from_device(self, t, kind, field):
+        a = self.engine.download(t)
+        return self.B.np_to_xfe(a, field) if kind == "x" else self.B.np_to_bfe(a[0], field)
+
+    # ------------------------------------------------------------------ code/ntt.py
+    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None):
+        n = len(values) if n_out is None else n_out
+        w = self.base_value(primitive_root, "primitive_root")
+        # every 2-power root of unity of F_p^3 lies in F_p, so a root with higher
+        # coefficients can never pass the order asserts of code/ntt.py:13-16
+        assert w is not None, "primitive root must be nth root of unity, where n is %d" % n
+        d, kind, field = self._to_device(values)
+        out = self.engine.ntt(d, _ilog2(n), w, offset=offset, inverse=inverse)
+        return self._from_device(out, kind, field)
+
+    def ntt(self, primitive_root, values):
+        """code/ntt.py:4-23"""
+        assert len(values) & (len(values) - 1) == 0, "cannot compute ntt of non-power-of-two sequence"
+        if len(values) <= 1:
+            return values  # the same list object, code/ntt.py:8-9
+        return self._transform(primitive_root, values, False)
+
+    def intt(self, primitive_root, values):
+        """code/ntt.py:26-42"""
+        n = len(values)
+        assert n & (n - 1) == 0, "cannot compute intt of non-power-of-two sequence"
+        w = self.base_value(primitive_root, "primitive_root")
+        assert w is not None and pow(w, n, P) == 1, "supplied root does not have supplied order"
+        if n == 1:
+            return values
+        assert n >= 2 and pow(w, n // 2, P) != 1, "supplied root is not primitive root of supplied order"
+        return self._transform(primitive_root, values, True)
+
+    def fast_coset_evaluate(self, polynomial, offset, generator, order):
+        """code/ntt.py:164-168: scale by offset, zero-pad to `order`, ntt -- one fused call"""
+        coeffs = polynomial.coefficients
+        m = len(coeffs)
+        if m == 0:
+            # nothing tells us the element class; the reference pads with offset.field.zero()
+            zero = offset.field.zero()
+            return self.ntt(generator, [zero] * order) if order > 1 else [zero] * order
+        assert order & (order - 1) == 0, "cannot compute ntt of non-power-of-two sequence"
+        assert m <= order, "polynomial has more coefficients than the domain has points"
+        off = self.base_value(offset, "offset")
+        if order <= 1:
+            return list(coeffs)  # offset^0 * c_0
+        if off is None:  # genuinely extension-field offset: scale kernel, then plain ntt
+            return self.ntt(generator, self.poly_scale(polynomial, offset).coefficients +
+                            [offset.field.zero()] * (order - m))
+        return self._transform(generator, coeffs, False, offset=off, n_out=order)
+
+    def fast_coset_interpolate(self, offset, generator, values):
+        """code/ntt.py:171-174: intt, then scale by offset^-1; all n coefficients are kept"""
+        n = len(values)
+        assert n & (n - 1) == 0, "cannot compute intt of non-power-of-two sequence"
+        w = self.base_value(generator, "generator")
+        assert w is not None and pow(w, n, P) == 1, "supplied root does not have supplied order"
+        Pn = self.B.Polynomial
+        if n == 1:
+            return Pn(values)  # offset^0
+        assert n >= 2 and pow(w, n // 2, P) != 1, "supplied root is not primitive root of supplied order"
+        off = self.base_value(offset, "offset")
+        if off is None:
+            return self.poly_scale(Pn(self.intt(generator, values)), offset.inverse())
+        assert off != 0, "divide by zero"
+        return Pn(self._transform(generator, values, True, offset=off))
+
+    # ------------------------------------------------------------------ code/univariate.py
+    def poly_scale(self, poly, factor):
+        """code/univariate.py:168-169"""
+        coeffs = poly.coefficients
+        Pn = self.B.Polynomial
+        if not coeffs:
+            return Pn([])
+        d, kind, field = self._to_device(coeffs)
+        if self.B.is_xfe(factor):
+            f = [c.value for c in factor.polynomial.coefficients]
+            f += [0] * (3 - len(f))
+            if kind == "b":
+                # (factor^i) * c_i with an extension factor and base coefficients: the reference's
+                # ExtensionField.multiply would fail on the BaseFieldElement operand
+                raise AttributeError("'BaseFieldElement' object has no attribute 'polynomial'")
+            out = self.engine.scale(d, f)
+            res_field = factor.field  # left operand of `(factor ^ i) * c`
+        else:
+            if kind == "x":
+                raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
+            out = self.engine.scale(d, factor.value)
+            res_field = factor.field
+        return Pn(self._from_device(out, kind, res_field))
+
+    def poly_evaluate_domain(self, poly, domain):
+        """code/univariate.py:153-154 on an arbitrary list of points"""
+        if len(domain) == 0:
+            return []
+        coeffs = poly.coefficients
+        first = domain[0]
+        if not coeffs:
+            return [d.field.zero() for d in domain]
+        dc, ck, _ = self._to_device(coeffs)
+        dp, pk, pfield = self._to_device(domain)
+        if ck == "x" and pk == "b":
+            raise AttributeError("'BaseFieldElement' object has no attribute 'polynomial'")
+        if ck == "b" and pk == "x":
+            raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
+        out = self.engine.eval_points(dc, dp)
+        # value = point.field.zero() + c * xi ...: results carry the point's field (code/univariate.py:146-150)
+        return self._from_device(out, "x" if pk == "x" else "b", pfield if pk == "x" else first.field)
+
+    # ------------------------------------------------------------------ code/fri.py Domain
+    def domain_evaluate(self, dom, polynomial):
+        """code/fri.py:26-30"""
+        coeffs = polynomial.coefficients
+        n = dom.length
+        if not coeffs:
+            zero = dom.omega.field.zero()
+            return self.ntt(dom.omega, [zero] * n)
+        assert len(coeffs) <= n, "polynomial has more coefficients than the domain has points"
+        if n <= 1:
+            return self.B.Polynomial(coeffs).scale(dom.offset).coefficients
+        w, off = dom.omega.value, dom.offset.value
+        d, kind, _ = self._to_device(coeffs)
+        if kind == "x":  # (offset ^ i) * c with a base-field offset, code/univariate.py:169
+            raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
+        out = self.engine.ntt(d, _ilog2(n), w, offset=off)
+        # scaled coefficients take offset.field (code/univariate.py:169); ntt keeps values[0].field
+        return self._from_device(out, kind, dom.offset.field if kind == "b" else coeffs[0].field)
+
+    def domain_xevaluate(self, dom, polynomial, xfield=None):
+        """code/fri.py:32-37"""
+        if xfield is None:
+            assert len(polynomial.coefficients) != 0, "trying to xevaluate zero polynomial with no target field"
+            xfield = polynomial.coefficients[0].field
+        return self.fast_coset_evaluate(polynomial, xfield.lift(dom.offset), xfield.lift(dom.omega), dom.length)
+
+    def domain_interpolate(self, dom, values):
+        """code/fri.py:39-40"""
+        return self.fast_coset_interpolate(dom.offset, dom.omega, values)
+
+    def domain_xinterpolate(self, dom, values):
+        """code/fri.py:42-44"""
+        xfield = values[0].field
+        return self.fast_coset_interpolate(xfield.lift(dom.offset), xfield.lift(dom.omega), values)
+
+    # ------------------------------------------------------------------ code/merkle.py
+    def merkle_build(self, tree, data_array, device_planes=None, device_nodes=None, leaf_cache=None,
+                     canonical=None):
+        """Body of Merkle.__init__ (code/merkle.py:8-41).  Sets the public attributes
+        num_leafs, depth, leafs, nodes on `tree`."""
+        n = len(data_array)
+        tree.num_leafs = n
+        npo2 = 1
+        while npo2 < n:
+            npo2 <<= 1
+        if n == 0:
+            npo2 = 0
+        tree.depth = _ilog2(npo2) if npo2 else 0  # code/merkle.py:16-20
+        tree.leafs = leaf_cache if leaf_cache is not None else [leaf for leaf in data_array]
+        if n == 0:
+            tree.nodes = []  # root() -> IndexError like the reference's nodes[1] on an empty list
+            return
+        eng = self.engine
+        if device_nodes is None:
+            first = tree.leafs[0]
+            planes = None
+            if canonical is None:
+                canonical = n == npo2 and self.B.is_xfe(first) and self.B.xfe_canonical(tree.leafs)
+            if canonical:
+                planes = device_planes if device_planes is not None else eng.upload(self.B.xfe_to_np(tree.leafs))
+                device_nodes = eng.merkle_field(planes, self.xfe_templates(first.field))
+            elif n == npo2 and self.B.is_bfe(first) and all(
+                    type(v) is self.B.BaseFieldElement and v.field is first.field for v in tree.leafs):
+                planes = eng.upload(self.B.bfe_to_np(tree.leafs))
+                device_nodes = eng.merkle_field(planes, self.bfe_templates(first.field))
+            else:  # arbitrary picklable leaves (code/test_merkle.py:57-61) or non-canonical identity
+                device_nodes = eng.merkle_blobs([pickle.dumps(leaf) for leaf in tree.leafs])
+            tree._planes = planes
+        else:
+            tree._planes = device_planes
+        tree._device_nodes = device_nodes
+        tree.nodes = NodeView(eng, device_nodes, npo2, n)
+
+    def merkle_open(self, tree, index):
+        """code/merkle.py:46-52"""
+        return tree.nodes.open(index, tree.depth)
+
+    # ------------------------------------------------------------------ code/fri.py Fri
+    def fri_commit(self, fri, codeword, proof_stream, round_index=0, Merkle=None):
+        """code/fri.py:91-139.  The round loop stays on the host because each challenge is a
+        hash of the pickled proof stream (code/fri.py:120 -> code/ip.py:21-22); per round the
+        device folds the codeword and builds the next tree in one fused call."""
+        B = self.B
+        xfield = fri.field
+        eng = self.engine
+        num_rounds = fri.num_rounds()
+        omega = self.base_value(fri.domain.omega)
+        offset = self.base_value(fri.domain.offset)
+        tpl = self.xfe_templates(xfield)
+        trees, codewords = [], []
+
+        N = len(codeword)
+        canonical = N > 0 and (N & (N - 1)) == 0 and B.is_xfe(codeword[0]) and B.xfe_canonical(codeword, xfield)
+        if N > 0 and not B.is_xfe(codeword[0]):
+            # code/fri.py:127: (one + alpha / ...) * codeword[i] needs extension-field elements
+            raise AttributeError("%r object has no attribute 'polynomial'" % type(codeword[0]).__name__)
+        planes = eng.upload(B.xfe_to_np(codeword)) if N > 0 else None
+        nodes = None
+        cache = None  # identity-stable objects of the current (device) codeword
+        for r in range(num_rounds):
+            N = len(codeword)
+            # code/fri.py:104-105
+            assert pow(omega, N - 1, P) == pow(omega, P - 2, P), "error in commit: omega does not have the right order!"
+            tree = Merkle.__new__(Merkle)
+            if r == 0:
+                self.merkle_build(tree, codeword, device_planes=planes, canonical=canonical)
+            else:
+                self.merkle_build(tree, codeword, device_planes=planes, device_nodes=nodes, leaf_cache=cache)
+            root = tree.root()
+            if r > 0:
+                proof_stream.push(root)
+            if r == num_rounds - 1:
+                break
+            alpha = xfield.sample(proof_stream.prover_fiat_shamir())
+            codewords.append(codeword)
+            trees.append(tree)
+            a = [c.value for c in alpha.polynomial.coefficients]
+            a += [0] * (3 - len(a))
+            planes, nodes = eng.fri_fold(planes, a, offset, omega, tpl)
+            cache = DeviceCodeword(self, planes, xfield)
+            codeword = cache
+            omega = omega * omega % P
+            offset = offset * offset % P
+        # send last codeword: a real list of real objects, shared with query_last (code/fri.py:134, :169)
+        if isinstance(codeword, DeviceCodeword):
+            codeword = codeword.materialize()
+        proof_stream.push(codeword)
+        codewords.append(codeword)
+        return codewords, trees
+
+    def fri_query(self, fri, current_tree, next_tree, c_indices, proof_stream):
+        """code/fri.py:141-158"""
+        half = len(current_tree.leafs) // 2
+        a_indices = [i for i in c_indices]
+        b_indices = [i + half for i in c_indices]
+        s = fri.num_colinearity_tests
+        prefetch(current_tree.leafs, a_indices[:s] + b_indices[:s])
+        prefetch(next_tree.leafs, c_indices[:s])
+        for k in range(s):
+            proof_stream.push((current_tree.leafs[a_indices[k]], current_tree.leafs[b_indices[k]],
+                               next_tree.leafs[c_indices[k]]))
+        prefetch_paths(current_tree, a_indices[:s] + b_indices[:s])
+        prefetch_paths(next_tree, c_indices[:s])
+        for k in range(s):
+            proof_stream.push(current_tree.open(a_indices[k]))
+            proof_stream.push(current_tree.open(b_indices[k]))
+            proof_stream.push(next_tree.open(c_indices[k]))
+        return a_indices + b_indices
+
+    def fri_query_last(self, fri, current_tree, last_codeword, c_indices, proof_stream):
+        """code/fri.py:160-176"""
+        half = len(current_tree.leafs) // 2
+        a_indices = [i for i in c_indices]
+        b_indices = [i + half for i in c_indices]
+        s = fri.num_colinearity_tests
+        prefetch(current_tree.leafs, a_indices[:s] + b_indices[:s])
+        for k in range(s):
+            proof_stream.push((current_tree.leafs[a_indices[k]], current_tree.leafs[b_indices[k]],
+                               last_codeword[c_indices[k]]))
+        prefetch_paths(current_tree, a_indices[:s] + b_indices[:s])
+        for k in range(s):
+            proof_stream.push(current_tree.open(a_indices[k]))
+            proof_stream.push(current_tree.open(b_indices[k]))
+        return a_indices + b_indices
+
+    def fri_prove(self, fri, codeword, proof_stream):
+        """code/fri.py:178-199"""
+        assert fri.domain.length == len(codeword), "initial codeword length does not match length of initial codeword"
+        codewords, trees = fri.commit(codeword, proof_stream)
+        top_level_indices = fri.sample_indices(proof_stream.prover_fiat_shamir(), len(codewords[1]),
+                                               len(codewords[-1]), fri.num_colinearity_tests)
+        indices = [i for i in top_level_indices]
+        for i in range(len(trees) - 1):
+            indices = [index % (len(codewords[i]) // 2) for index in indices]
+            fri.query(trees[i], trees[i + 1], indices, proof_stream)
+        indices = [index % len(codewords[-1]) for index in indices]
+        fri.query_last(trees[-1], codewords[-1], indices, proof_stream)
+        return top_level_indices
+
+
+def prefetch(leafs, indices):
+    if isinstance(leafs, DeviceCodeword):
+        leafs.prefetch(indices)
+
+
+def prefetch_paths(tree, indices):
+    nodes = getattr(tree, "nodes", None)
+    if isinstance(nodes, NodeView):
+        nodes.prefetch_paths(indices, tree.depth)
+
+
+class DeviceCodeword:
+    """A folded FRI codeword that lives on the device.  Behaves like the list of
+    ExtensionFieldElements the reference builds at code/fri.py:127-128 for the accesses the
+    reference makes (len, indexing, iteration); elements are materialised on demand and
+    cached, so repeated access returns the SAME object (pickle memoises by identity,
+    SURVEY B5 rule 3)."""
+
+    def __init__(self, glue, planes, xfield):
+        self._glue = glue
+        self._planes = planes
+        self._xfield = xfield
+        self._n = planes.shape[1]
+        self._cache = {}
+
+    def __len__(self):
+        return self._n
+
+    def prefetch(self, indices):
+        need = [i for i in dict.fromkeys(indices) if i not in self._cache]
+        if not need:
+            return
+        for i in need:
+            if not 0 <= i < self._n:
+                raise IndexError("list index out of range")
+        vals = self._glue.engine.gather(self._planes, need)
+        mk, xf = self._glue.B.make_xfe, self._xfield
+        for i, v in zip(need, vals.tolist()):
+            self._cache[i] = mk(v[0], v[1], v[2], xf)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if i not in self._cache:
+            self.prefetch([i])
+        return self._cache[i]
+
+    def __iter__(self):
+        return iter(self.materialize())
+
+    def materialize(self):
+        """the whole codeword as a real list (cached objects are reused)"""
+        if len(self._cache) < self._n:
+            a = self._glue.engine.download(self._planes)
+            mk, xf = self._glue.B.make_xfe, self._xfield
+            c0, c1, c2 = a[0].tolist(), a[1].tolist(), a[2].tolist()
+            for i in range(self._n):
+                if i not in self._cache:
+                    self._cache[i] = mk(c0[i], c1[i], c2[i], xf)
+        return [self._cache[i] for i in range(self._n)]
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+
+class NodeView:
+    """Merkle.nodes for a tree whose digests live on the device (code/merkle.py:26-41 heap
+    layout).  Indexing returns `bytes` objects that are cached, so auth paths of different
+    leaves share their upper siblings exactly like slices of the reference's list."""
+
+    _ZERO32 = bytes(32)
+
+    def __init__(self, engine, device_nodes, npo2, n_leafs):
+        self._eng = engine
+        self._dev = device_nodes
+        self._npo2 = npo2
+        self._n = n_leafs
+        self._cache = {}
+
+    def __len__(self):
+        return 2 * self._npo2
+
+    def _fetch_all(self):
+        raw = self._eng.download_bytes(self._dev)
+        for k in range(1, 2 * self._npo2):
+            if k not in self._cache and not (k >= self._npo2 + self._n):
+                self._cache[k] = raw[64 * k:64 * k + 64]
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            self._fetch_all()
+            return [self[j] for j in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError("list index out of range")
+        if k >= self._npo2 + self._n:
+            return self._ZERO32  # unused leaf slot, code/merkle.py:26
+        v = self._cache.get(k)
+        if v is None:
+            if k == 0:
+                # code/merkle.py:35-41 also overwrites slot 0 with blake2b(placeholder | root)
+                from hashlib import blake2b
+                v = blake2b(self._ZERO32 + self[1]).digest() if self._npo2 >= 1 else self._ZERO32
+            else:
+                v = self._eng.download_bytes(self._dev[k])
+            self._cache[k] = v
+        return v
+
+    def __iter__(self):
+        self._fetch_all()
+        return (self[k] for k in range(len(self)))
+
+    def prefetch_paths(self, indices, depth):
+        if depth == 0:
+            return
+        need = [i for i in dict.fromkeys(indices)
+                if any((((1 << depth) | i) >> j) ^ 1 not in self._cache for j in range(depth))]
+        need = [i for i in need if 0 <= i < (1 << depth)]
+        if not need:
+            return
+        paths = self._eng.merkle_open(self._dev, need)
+        for i, path in zip(need, paths):
+            k = (1 << depth) | i
+            for j in range(depth):
+                sib = (k >> j) ^ 1
+                if sib not in self._cache and not (sib >= self._npo2 + self._n):
+                    self._cache[sib] = path[j]
+
+    def open(self, index, depth):
+        """code/merkle.py:46-52"""
+        self.prefetch_paths([index], depth)
+        path = []
+        k = (1 << depth) | index
+        while k > 1:
+            path += [self[k ^ 1]]
+            k >>= 1
+        return path

@@ -1,0 +1,263 @@
+"""GPU parity, array level: every C-ABI entry point against the CPU oracle on seeded inputs
+and against the golden digests produced by the unmodified reference."""
+import hashlib
+import pickle
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as orc  # noqa: E402
+from util import P, bfe_digest, golden, have_golden, rand_bfe, rand_xfe, root_of_unity, xfe_digest  # noqa: E402
+
+S = golden("small.json")
+M = golden("merkle.json")
+F = golden("fold.json")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from stark_brainfuck_b200 import Engine
+    return Engine(0)
+
+
+def tpl_pair():
+    from stark_brainfuck_b200.marshal import templates_from_marker_pickles
+    x = templates_from_marker_pickles([bytes.fromhex(M["xfe_marker_pickles"][str(k)]) for k in range(4)], 3, True)
+    b = templates_from_marker_pickles([bytes.fromhex(M["bfe_marker_pickle"])], 1, False)
+    return x, b
+
+
+@pytest.mark.parametrize("logn", list(range(0, 23)))
+def test_ntt_bfe_vs_oracle(eng, logn):
+    n = 1 << logn
+    x = rand_bfe(logn, n)
+    w = root_of_unity(logn) if logn else 1
+    d = eng.upload(x)
+    y = eng.download(eng.ntt(d, logn, w))[0]
+    assert np.array_equal(y, orc.ntt(w, x))
+    z = eng.download(eng.ntt(d, logn, w, inverse=True))[0]
+    assert np.array_equal(z, orc.intt(w, x))
+    # bit-exact round trip, in place
+    t = eng.ntt(d, logn, w)
+    eng.ntt(t, logn, w, inverse=True, out=t)
+    assert np.array_equal(eng.download(t)[0], x)
+    e = S["ntt_bfe"].get(str(logn))
+    if e:
+        assert bfe_digest(y) == e["ntt_digest"] and bfe_digest(z) == e["intt_digest"]
+
+
+@pytest.mark.parametrize("logn", (16, 18, 20))
+def test_ntt_bfe_big_golden(eng, logn):
+    g = golden("ntt_big.json")
+    if str(logn) not in g:
+        pytest.skip("golden not generated")
+    x = rand_bfe(logn, 1 << logn)
+    w = root_of_unity(logn)
+    d = eng.upload(x)
+    assert bfe_digest(eng.download(eng.ntt(d, logn, w))[0]) == g[str(logn)]["ntt_digest"]
+    if "intt_digest" in g[str(logn)]:
+        assert bfe_digest(eng.download(eng.ntt(d, logn, w, inverse=True))[0]) == g[str(logn)]["intt_digest"]
+
+
+@pytest.mark.parametrize("logn", list(range(1, 13)) + [14, 16, 18])
+def test_ntt_xfe_golden(eng, logn):
+    e = S["ntt_xfe"].get(str(logn)) or (golden("xntt_big.json").get(str(logn)) if have_golden("xntt_big.json") else None)
+    x = rand_xfe(100 + logn, 1 << logn)
+    w = root_of_unity(logn)
+    y = eng.download(eng.ntt(eng.upload(x), logn, w))
+    assert np.array_equal(y, orc.xntt(w, x))
+    if e:
+        assert xfe_digest(y) == e["ntt_digest"]
+
+
+def test_ntt_other_roots_and_asserts(eng):
+    # any primitive root must work, not only the canonical one
+    for logn in (3, 7, 11, 13):
+        n = 1 << logn
+        w = pow(root_of_unity(logn), 5, P)
+        x = rand_bfe(50 + logn, n)
+        assert np.array_equal(eng.download(eng.ntt(eng.upload(x), logn, w))[0], orc.ntt(w, x))
+    d = eng.upload(rand_bfe(1, 8))
+    with pytest.raises(AssertionError):
+        eng.ntt(d, 3, root_of_unity(4))  # order 16
+    with pytest.raises(AssertionError):
+        eng.ntt(d, 3, root_of_unity(2))  # not primitive
+
+
+@pytest.mark.parametrize("logn,m", [(3, 2), (3, 8), (6, 16), (6, 17), (9, 128), (9, 512), (11, 512), (11, 513),
+                                     (11, 2048), (14, 4096), (17, 1 << 15), (20, 1 << 18)])
+def test_coset_evaluate_interpolate(eng, logn, m):
+    n = 1 << logn
+    w = root_of_unity(logn)
+    c = rand_bfe(300 + logn, m)
+    y = eng.download(eng.ntt(eng.upload(c), logn, w, offset=7))[0]
+    assert np.array_equal(y, orc.coset_evaluate(7, w, c, n))
+    key = "%d_%d" % (logn, m)
+    if key in S["coset"]:
+        assert bfe_digest(y) == S["coset"][key]["evaluate_digest"]
+    xc = rand_xfe(400 + logn, m)
+    xy = eng.download(eng.ntt(eng.upload(xc), logn, w, offset=7))
+    assert np.array_equal(xy, orc.coset_evaluate(7, w, xc, n))
+    if key in S["coset"]:
+        assert xfe_digest(xy) == S["coset"][key]["xevaluate_digest"]
+    if m == n:
+        v = rand_bfe(500 + logn, n)
+        ip = eng.download(eng.ntt(eng.upload(v), logn, w, offset=7, inverse=True))[0]
+        assert np.array_equal(ip, orc.coset_interpolate(7, w, v))
+        if "interpolate_digest" in S["coset"].get(key, {}):
+            assert bfe_digest(ip) == S["coset"][key]["interpolate_digest"]
+    # evaluate then interpolate returns the zero-padded coefficients
+    back = eng.download(eng.ntt(eng.upload(y), logn, w, offset=7, inverse=True))[0]
+    assert np.array_equal(back[:m], c) and not back[m:].any()
+
+
+def test_batched_planes(eng):
+    logn, q = 12, 7
+    n = 1 << logn
+    w = root_of_unity(logn)
+    x = np.stack([rand_bfe(60 + i, n) for i in range(q)])
+    y = eng.download(eng.ntt(eng.upload(x), logn, w, offset=7))
+    for i in range(q):
+        assert np.array_equal(y[i], orc.coset_evaluate(7, w, x[i], n))
+
+
+def test_scale_and_eval_points(eng):
+    c = rand_bfe(701, 37)
+    f = S["scale_bfe"]["factor"]
+    assert bfe_digest(eng.download(eng.scale(eng.upload(c), f))[0]) == S["scale_bfe"]["digest"]
+    xc = rand_xfe(702, 29)
+    assert xfe_digest(eng.download(eng.scale(eng.upload(xc), S["scale_xfe"]["factor"]))) == S["scale_xfe"]["digest"]
+    pts = rand_bfe(703, 50)
+    assert bfe_digest(eng.download(eng.eval_points(eng.upload(c), eng.upload(pts)))[0]) == \
+        S["evaluate_domain_bfe"]["digest"]
+    xpts = rand_xfe(704, 41)
+    assert xfe_digest(eng.download(eng.eval_points(eng.upload(xc), eng.upload(xpts)))) == \
+        S["evaluate_domain_xfe"]["digest"]
+    # mixed shapes against the oracle
+    got = eng.download(eng.eval_points(eng.upload(xc), eng.upload(pts)))
+    lifted = np.zeros((3, 50), dtype=np.uint64)
+    lifted[0] = pts
+    assert np.array_equal(got, orc.eval_points(xc, lifted))
+    got = eng.download(eng.eval_points(eng.upload(c), eng.upload(xpts)))
+    cl = np.zeros((3, 37), dtype=np.uint64)
+    cl[0] = c
+    assert np.array_equal(got, orc.eval_points(cl, xpts))
+
+
+def mixed_tree_values(logn):
+    from test_oracle import tree_values
+    return tree_values(logn)
+
+
+@pytest.mark.parametrize("logn", list(range(0, 11)) + [13, 16])
+def test_merkle_field_trees(eng, logn):
+    xt, bt = tpl_pair()
+    if logn <= 10:
+        planes = mixed_tree_values(logn)
+    else:
+        planes = rand_xfe(100 + logn, 1 << logn)
+    n = 1 << logn
+    nodes = eng.download_bytes(eng.merkle_field(eng.upload(planes), xt))
+    ref = orc.merkle_field(orc.templates_from_marker_pickles(
+        [bytes.fromhex(M["xfe_marker_pickles"][str(k)]) for k in range(4)], 3, True), planes)
+    assert nodes[64:] == ref[1:].tobytes()
+    if logn <= 10:
+        assert nodes[64:128].hex() == M["xfe_trees"][str(logn)]["root"]
+        assert hashlib.sha256(nodes[64:]).hexdigest() == M["xfe_trees"][str(logn)]["nodes_sha256"]
+    bn = eng.download_bytes(eng.merkle_field(eng.upload(planes[0].copy()), bt))
+    if logn <= 10:
+        assert bn[64:128].hex() == M["bfe_trees"][str(logn)]["root"]
+        assert hashlib.sha256(bn[64:]).hexdigest() == M["bfe_trees"][str(logn)]["nodes_sha256"]
+    # openings
+    d_nodes = eng.merkle_field(eng.upload(planes), xt)
+    idx = sorted({0, n - 1, n // 3})
+    paths = eng.merkle_open(d_nodes, idx)
+    for i, p in zip(idx, paths):
+        assert p == orc.merkle_open(ref, i)
+
+
+def test_merkle_gv2_and_uniform(eng):
+    xt, _ = tpl_pair()
+    g = M["gv2"]
+    planes = np.array(g["leaves"], dtype=np.uint64).T.copy()
+    d = eng.merkle_field(eng.upload(planes), xt)
+    assert eng.root(d).hex() == g["root"]
+    assert [b.hex() for b in eng.merkle_open(d, [2])[0]] == g["open2"]
+    for logn, e in M["xfe_trees_uniform"].items():
+        d = eng.merkle_field(eng.upload(rand_xfe(100 + int(logn), 1 << int(logn))), xt)
+        assert eng.root(d).hex() == e["root"]
+
+
+@pytest.mark.parametrize("n", (1, 2, 3, 5, 8, 13, 64, 100))
+def test_merkle_blobs(eng, n):
+    from test_oracle import blob_leaves
+    e = M["blob_trees"][str(n)]
+    blobs = [pickle.dumps(x) for x in blob_leaves(n)]
+    d = eng.merkle_blobs(blobs)
+    assert eng.root(d).hex() == e["root"]
+    ref = orc.merkle_blobs(blobs)
+    got = np.frombuffer(eng.download_bytes(d), dtype=np.uint8).reshape(-1, 64)
+    npo2 = got.shape[0] // 2
+    for k in range(1, npo2 + n):
+        assert bytes(got[k]) == bytes(ref[k]), k
+
+
+def test_merkle_blob_lengths(eng):
+    R = random.Random(7)
+    blobs = [bytes(R.getrandbits(8) for _ in range(L)) for L in list(range(0, 140)) + [255, 256, 257, 383, 384, 385, 1000]]
+    d = eng.merkle_blobs(blobs)
+    got = np.frombuffer(eng.download_bytes(d), dtype=np.uint8).reshape(-1, 64)
+    npo2 = got.shape[0] // 2
+    for i, b in enumerate(blobs):
+        assert bytes(got[npo2 + i]) == hashlib.blake2b(b).digest(), len(b)
+
+
+@pytest.mark.parametrize("logn", (1, 2, 4, 6, 8, 12, 17))
+def test_fri_fold(eng, logn):
+    xt, _ = tpl_pair()
+    n = 1 << logn
+    cw = rand_xfe(1100 + logn, n)
+    R = random.Random(1100 + logn)  # make_golden.py draws alpha from a fresh Random(seed)
+    alpha = [R.randrange(P) for _ in range(3)]
+    w = root_of_unity(logn)
+    nxt, nodes = eng.fri_fold(eng.upload(cw), alpha, 7, w, xt)
+    ref = orc.fri_fold(cw, alpha, 7, w)
+    assert np.array_equal(eng.download(nxt), ref)
+    e = F.get("fold_%d" % logn)
+    if e:
+        assert alpha == e["alpha"] and xfe_digest(ref) == e["digest"]
+    otpl = orc.templates_from_marker_pickles(
+        [bytes.fromhex(M["xfe_marker_pickles"][str(k)]) for k in range(4)], 3, True)
+    assert eng.download_bytes(nodes)[64:] == orc.merkle_field(otpl, ref)[1:].tobytes()
+    nxt2, none = eng.fri_fold(eng.upload(cw), alpha, 7, w, None)
+    assert none is None and np.array_equal(eng.download(nxt2), ref)
+    # structured input: a zero codeword folds to zeros (k = 0 leaf template)
+    z = np.zeros((3, n), dtype=np.uint64)
+    nz, nn = eng.fri_fold(eng.upload(z), alpha, 7, w, xt)
+    assert not eng.download(nz).any()
+    assert eng.download_bytes(nn)[64:] == orc.merkle_field(otpl, np.zeros((3, n // 2), dtype=np.uint64))[1:].tobytes()
+
+
+def test_gather(eng):
+    x = rand_xfe(9, 1000)
+    idx = [0, 999, 5, 5, 123]
+    got = eng.gather(eng.upload(x), idx)
+    assert np.array_equal(got, x[:, idx].T)
+
+
+def test_ntt_host_path(eng):
+    import torch
+    logn = 14
+    x = rand_bfe(logn, 1 << logn)
+    h = torch.from_numpy(x.view(np.int64).reshape(1, -1).copy()).pin_memory()
+    out = eng.ntt_host(h, logn, root_of_unity(logn))
+    assert np.array_equal(out.numpy().view(np.uint64)[0], orc.ntt(root_of_unity(logn), x))
+
+
+def test_launch_counter_moves(eng):
+    a = eng.launch_count()
+    eng.ntt(eng.upload(rand_bfe(1, 64)), 6, root_of_unity(6))
+    assert eng.launch_count() > a
