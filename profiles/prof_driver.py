@@ -1,0 +1,35 @@
+"""Small driver for ncu captures: a few launches of each hot kernel (not a benchmark)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+from util import rand_bfe, rand_xfe, root_of_unity  # noqa: E402
+from stark_brainfuck_b200 import Engine, mirror  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+eng = Engine(0)
+logn = 20
+n = 1 << logn
+w = root_of_unity(logn)
+x = eng.upload(rand_bfe(1, n))
+y = eng.empty(1, n)
+if what in ("all", "ntt"):
+    for _ in range(3):
+        eng.ntt(x, logn, w, out=y)
+        eng.ntt(y, logn, w, inverse=True, out=y)
+    xb = torch.randint(0, 2 ** 62, (32, n), dtype=torch.int64, device=eng.device)
+    yb = eng.empty(32, n)
+    for _ in range(2):
+        eng.ntt(xb, logn, w, offset=7, out=yb)
+if what in ("all", "fri"):
+    mirror.register()
+    tpl = mirror.binding.xfe_templates(mirror.xfield)
+    cw = eng.upload(rand_xfe(2, 1 << 18))
+    for _ in range(2):
+        nodes = eng.merkle_field(cw, tpl)
+        nxt, nn = eng.fri_fold(cw, [3, 5, 7], 7, root_of_unity(18), tpl)
+torch.cuda.synchronize()
+print("launches", eng.launch_count())

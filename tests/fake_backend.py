@@ -1,0 +1,150 @@
+"""TEST-ONLY stand-in for libb2s.so: the same C-ABI entry points (include/b2s.h) executed by the
+CPU oracle on HOST memory, so that the host glue (marshalling, identity rules, FRI round loop,
+drop-in patching) can be exercised in a container without a GPU.
+
+It is injected explicitly (`Engine(lib=FakeLib(), device="cpu")`) by tests; nothing in
+stark_brainfuck_b200/ knows about it and the product path never falls back to it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from oracle import oracle as orc
+
+ERR_ROOT, ERR_PRIM = -11, -12
+
+
+def _addr(p):
+    if p is None:
+        return 0
+    if isinstance(p, int):
+        return p
+    return p.value or 0
+
+
+def _u64(addr, count):
+    return np.ctypeslib.as_array((C.c_uint64 * count).from_address(addr))
+
+
+def _u8(addr, count):
+    return np.ctypeslib.as_array((C.c_uint8 * count).from_address(addr))
+
+
+def _otpl(tp):
+    src = tp._obj if hasattr(tp, "_obj") else tp.contents
+    dst = orc.LeafTemplates()
+    assert C.sizeof(dst) == C.sizeof(src)
+    C.memmove(C.byref(dst), C.byref(src), C.sizeof(src))
+    return dst
+
+
+class FakeLib:
+    def __init__(self):
+        self.launches = 0
+        self.err = b""
+
+    def b2s_last_error(self):
+        return self.err
+
+    def b2s_launch_count(self):
+        return self.launches
+
+    def b2s_ntt(self, d_in, in_stride, n_in, d_out, out_stride, log_n, q, omega, offset, inverse, stream):
+        n = 1 << log_n
+        P = orc.P
+        if pow(omega, n, P) != 1:
+            self.err = b"primitive root must be nth root of unity"
+            return ERR_ROOT
+        if log_n >= 1 and pow(omega, n // 2, P) == 1:
+            self.err = b"primitive root is not primitive nth root of unity"
+            return ERR_PRIM
+        self.launches += 1
+        ins = [_u64(_addr(d_in) + 8 * in_stride * i, n_in).copy() for i in range(q)]
+        for i in range(q):
+            out = _u64(_addr(d_out) + 8 * out_stride * i, n)
+            if inverse:
+                out[:] = orc.coset_interpolate(offset, omega, ins[i]) if n > 1 else ins[i]
+            else:
+                out[:] = orc.coset_evaluate(offset, omega, ins[i], n) if n > 1 else ins[i]
+        return 0
+
+    def b2s_ntt_host(self, h_in, in_stride, n_in, h_out, out_stride, log_n, q, omega, offset, inverse):
+        return self.b2s_ntt(h_in, in_stride, n_in, h_out, out_stride, log_n, q, omega, offset, inverse, None)
+
+    def b2s_scale(self, d_in, in_stride, d_out, out_stride, n, q, factor, stream):
+        self.launches += 1
+        if q == 1:
+            _u64(_addr(d_out), n)[:] = orc.scale(int(factor[0]), _u64(_addr(d_in), n))
+        else:
+            x = np.stack([_u64(_addr(d_in) + 8 * in_stride * i, n) for i in range(3)])
+            r = orc.xscale([int(factor[i]) for i in range(3)], x)
+            for i in range(3):
+                _u64(_addr(d_out) + 8 * out_stride * i, n)[:] = r[i]
+        return 0
+
+    def b2s_eval_points(self, d_c, cstride, cq, m, d_p, pstride, pq, k, d_out, ostride, stream):
+        self.launches += 1
+        c = np.zeros((3, m), dtype=np.uint64)
+        p = np.zeros((3, k), dtype=np.uint64)
+        for i in range(cq):
+            c[i] = _u64(_addr(d_c) + 8 * cstride * i, m)
+        for i in range(pq):
+            p[i] = _u64(_addr(d_p) + 8 * pstride * i, k)
+        if cq == 1 and pq == 1:
+            _u64(_addr(d_out), k)[:] = orc.eval_points(c[0], p[0])
+        else:
+            r = orc.eval_points(c, p)
+            for i in range(3):
+                _u64(_addr(d_out) + 8 * ostride * i, k)[:] = r[i]
+        return 0
+
+    def b2s_merkle_field(self, d_planes, stride, n, tpl, d_nodes, stream):
+        self.launches += 1
+        t = _otpl(tpl)
+        planes = np.stack([_u64(_addr(d_planes) + 8 * stride * i, n) for i in range(t.n_slots)])
+        nodes = orc.merkle_field(t, planes if t.n_slots == 3 else planes[0])
+        _u8(_addr(d_nodes), 128 * n)[:] = nodes.reshape(-1)
+        return 0
+
+    def b2s_merkle_blobs(self, d_bytes, d_offsets, n, npo2, d_nodes, stream):
+        self.launches += 1
+        offs = _u64(_addr(d_offsets), n + 1)
+        data = _u8(_addr(d_bytes), int(offs[n])) if offs[n] else np.zeros(0, dtype=np.uint8)
+        blobs = [bytes(data[int(offs[i]):int(offs[i + 1])]) for i in range(n)]
+        _u8(_addr(d_nodes), 128 * npo2)[:] = orc.merkle_blobs(blobs).reshape(-1)
+        return 0
+
+    def b2s_merkle_open(self, d_nodes, npo2, h_idx, n_idx, h_paths, stream):
+        self.launches += 1
+        nodes = _u8(_addr(d_nodes), 128 * npo2).reshape(-1, 64)
+        idx = _u64(_addr(h_idx), n_idx)
+        depth = npo2.bit_length() - 1
+        out = _u8(_addr(h_paths), n_idx * depth * 64).reshape(n_idx, depth, 64)
+        for q in range(n_idx):
+            for j, b in enumerate(orc.merkle_open(nodes, int(idx[q]))):
+                out[q, j] = np.frombuffer(b, dtype=np.uint8)
+        return 0
+
+    def b2s_fri_fold(self, d_cw, cw_stride, N, alpha, offset, omega, d_next, next_stride, tpl, d_next_nodes, stream):
+        self.launches += 1
+        cw = np.stack([_u64(_addr(d_cw) + 8 * cw_stride * i, N) for i in range(3)])
+        r = orc.fri_fold(cw, [int(alpha[i]) for i in range(3)], offset, omega)
+        for i in range(3):
+            _u64(_addr(d_next) + 8 * next_stride * i, N // 2)[:] = r[i]
+        if _addr(d_next_nodes):
+            _u8(_addr(d_next_nodes), 64 * N)[:] = orc.merkle_field(_otpl(tpl), r).reshape(-1)
+        return 0
+
+    def b2s_gather(self, d_planes, stride, q, h_idx, n_idx, h_out, stream):
+        self.launches += 1
+        idx = _u64(_addr(h_idx), n_idx)
+        out = _u64(_addr(h_out), n_idx * q).reshape(n_idx, q)
+        for pl in range(q):
+            col = _u64(_addr(d_planes) + 8 * stride * pl, int(idx.max()) + 1)
+            out[:, pl] = col[idx.astype(np.int64)]
+        return 0
+
+
+def fake_engine():
+    from stark_brainfuck_b200 import Engine
+    return Engine(lib=FakeLib(), device="cpu")

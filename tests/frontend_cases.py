@@ -1,0 +1,276 @@
+"""Front-end parity cases shared by the three environments:
+   reference + drop-in + test backend (CPU), mirror + test backend (CPU), mirror + libb2s.so (GPU).
+Each case takes `env`, a namespace with the reference-named classes/functions."""
+import hashlib
+import pickle
+import random
+import types
+
+import numpy as np
+import pytest
+
+from util import P, bfe_digest, golden, have_golden, xfe_digest
+
+S = golden("small.json")
+M = golden("merkle.json")
+FS = golden("fri_small.json")
+
+
+def make_env(algebra, univariate, extension_field, ntt, merkle, ip, fri):
+    env = types.SimpleNamespace()
+    env.BaseField, env.BaseFieldElement = algebra.BaseField, algebra.BaseFieldElement
+    env.Polynomial = univariate.Polynomial
+    env.ExtensionField, env.ExtensionFieldElement = extension_field.ExtensionField, extension_field.ExtensionFieldElement
+    env.ntt, env.intt = ntt.ntt, ntt.intt
+    env.fast_coset_evaluate, env.fast_coset_interpolate = ntt.fast_coset_evaluate, ntt.fast_coset_interpolate
+    env.fast_multiply = ntt.fast_multiply
+    env.Merkle, env.ProofStream, env.Fri = merkle.Merkle, ip.ProofStream, fri.Fri
+    env.field = env.BaseField.main()
+    env.xfield = env.ExtensionField.main()
+    env.xbf = env.xfield.modulus.coefficients[0].field
+    return env
+
+
+def vals(xs):
+    return [x.value for x in xs]
+
+
+def triples(xs):
+    out = []
+    for x in xs:
+        c = [co.value for co in x.polynomial.coefficients]
+        out.append(c + [0] * (3 - len(c)))
+    return out
+
+
+def bdig(xs):
+    return bfe_digest(np.array(vals(xs), dtype=np.uint64))
+
+
+def xdig(xs):
+    return xfe_digest(np.array(triples(xs), dtype=np.uint64).T.reshape(3, -1))
+
+
+def X(env, *c):
+    return env.ExtensionFieldElement(env.Polynomial([env.BaseFieldElement(v, env.xbf) for v in c]), env.xfield)
+
+
+def rand_bfe_list(env, seed, n):
+    R = random.Random(seed)
+    return [env.BaseFieldElement(R.randrange(P), env.field) for _ in range(n)]
+
+
+def rand_xfe_list(env, seed, n):
+    R = random.Random(seed)
+    return [X(env, R.randrange(P), R.randrange(P), R.randrange(P)) for _ in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------
+def case_ntt_golden(env, max_log=12):
+    w8 = env.field.primitive_nth_root(8)
+    v = [env.BaseFieldElement(i, env.field) for i in range(1, 9)]
+    y = env.ntt(w8, v)
+    assert vals(y) == S["gv1_ntt8"] and vals(env.intt(w8, y)) == list(range(1, 9))
+    assert all(type(t) is env.BaseFieldElement and t.field is env.field for t in y)
+    for logn in range(1, max_log + 1):
+        n = 1 << logn
+        w = env.field.primitive_nth_root(n)
+        x = rand_bfe_list(env, logn, n)
+        e = S["ntt_bfe"][str(logn)]
+        assert bdig(env.ntt(w, x)) == e["ntt_digest"]
+        assert bdig(env.intt(w, x)) == e["intt_digest"]
+    for logn in range(1, min(max_log, 12) + 1):
+        n = 1 << logn
+        w = env.xfield.lift(env.field.primitive_nth_root(n))
+        x = rand_xfe_list(env, 100 + logn, n)
+        y = env.ntt(w, x)
+        assert xdig(y) == S["ntt_xfe"][str(logn)]["ntt_digest"]
+        assert all(t.field is env.xfield for t in y)
+        assert all(c.field is env.xbf for t in y for c in t.polynomial.coefficients)
+
+
+def case_ntt_quirks(env):
+    f = env.field
+    one_elem = [f(5)]
+    assert env.ntt(f.primitive_nth_root(2), one_elem) is one_elem  # code/ntt.py:8-9
+    empty = []
+    assert env.ntt(f.primitive_nth_root(2), empty) is empty
+    assert env.intt(f.one(), one_elem) is one_elem  # code/ntt.py:32-33
+    with pytest.raises(AssertionError):
+        env.ntt(f.primitive_nth_root(8), [f(i) for i in range(6)])
+    with pytest.raises(AssertionError):
+        env.ntt(f.primitive_nth_root(16), [f(i) for i in range(8)])
+    with pytest.raises(AssertionError):
+        env.ntt(f.primitive_nth_root(4), [f(i) for i in range(8)])
+    with pytest.raises(AssertionError):
+        env.intt(f.primitive_nth_root(4), [f(i) for i in range(8)])
+    with pytest.raises(AssertionError):
+        env.intt(f.primitive_nth_root(16), [f(i) for i in range(8)])
+
+
+def case_coset_and_poly(env):
+    Fri = env.Fri
+    for key, e in S["coset"].items():
+        logn, m = (int(t) for t in key.split("_"))
+        n = 1 << logn
+        dom = Fri.Domain(env.field.generator(), env.field.primitive_nth_root(n), n)
+        poly = env.Polynomial(rand_bfe_list(env, 300 + logn, m))
+        ev = dom.evaluate(poly)
+        assert bdig(ev) == e["evaluate_digest"] and len(poly.coefficients) == m
+        xev = dom.xevaluate(env.Polynomial(rand_xfe_list(env, 400 + logn, m)), env.xfield)
+        assert xdig(xev) == e["xevaluate_digest"]
+        if "interpolate_digest" in e:
+            ip = dom.interpolate(rand_bfe_list(env, 500 + logn, n))
+            assert type(ip) is env.Polynomial and len(ip.coefficients) == e["interpolate_len"]
+            assert bdig(ip.coefficients) == e["interpolate_digest"]
+            xip = dom.xinterpolate(rand_xfe_list(env, 600 + logn, n))
+            assert xdig(xip.coefficients) == e["xinterpolate_digest"]
+    two = env.BaseFieldElement(2, env.field)
+    poly = env.Polynomial(rand_bfe_list(env, 777, 300))
+    assert bdig(env.fast_coset_evaluate(poly, two, env.field.primitive_nth_root(512), 512)) == \
+        S["coset_offset2"]["digest"]
+    # Polynomial.scale / evaluate_domain
+    poly = env.Polynomial(rand_bfe_list(env, 701, 37))
+    sc = poly.scale(env.BaseFieldElement(S["scale_bfe"]["factor"], env.field))
+    assert type(sc) is env.Polynomial and bdig(sc.coefficients) == S["scale_bfe"]["digest"]
+    xpoly = env.Polynomial(rand_xfe_list(env, 702, 29))
+    assert xdig(xpoly.scale(X(env, *S["scale_xfe"]["factor"])).coefficients) == S["scale_xfe"]["digest"]
+    assert bdig(poly.evaluate_domain(rand_bfe_list(env, 703, 50))) == S["evaluate_domain_bfe"]["digest"]
+    assert xdig(xpoly.evaluate_domain(rand_xfe_list(env, 704, 41))) == S["evaluate_domain_xfe"]["digest"]
+    assert poly.evaluate_domain([]) == []
+    # fast_multiply rides on the patched ntt/intt (code/ntt.py:45-79)
+    a = env.Polynomial(rand_bfe_list(env, 31, 20))
+    b = env.Polynomial(rand_bfe_list(env, 32, 25))
+    fm = env.fast_multiply(a, b, env.field.primitive_nth_root(64), 64)
+    assert vals(fm.coefficients) == vals((a * b).coefficients)
+
+
+def case_merkle(env):
+    Merkle = env.Merkle
+    g = M["gv2"]
+    leaves = [X(env, *[v for v in c][:k]) for c, k in zip(g["leaves"], (3, 3, 1, 0))]
+    t = Merkle(leaves)
+    assert t.root().hex() == g["root"] and [b.hex() for b in t.open(2)] == g["open2"]
+    assert t.num_leafs == 4 and t.depth == 2 and len(t.nodes) == 8
+    assert [t.nodes[k].hex() for k in range(8)] == g["nodes"]
+    assert t.leafs[1] is leaves[1] and t.nodes[3] is t.nodes[3] and t.open(0)[1] is t.open(1)[1]
+    for i in range(4):
+        assert Merkle.verify(t.root(), i, t.open(i), leaves[i])
+    assert not Merkle.verify(t.root(), 1, t.open(1), leaves[2])
+    # base-field leaves
+    from test_oracle import blob_leaves, tree_values
+    for logn in (0, 1, 5, 8):
+        planes = tree_values(logn)
+        bl = [env.BaseFieldElement(int(v), env.field) for v in planes[0]]
+        assert Merkle(bl).root().hex() == M["bfe_trees"][str(logn)]["root"]
+        xl = [X(env, *[int(planes[j][i]) for j in range(3)]) for i in range(1 << logn)]
+        # X() does not trim; the constructor does (code/extension_field.py:6-9)
+        tx = Merkle(xl)
+        assert tx.root().hex() == M["xfe_trees"][str(logn)]["root"]
+        assert [b.hex() for b in tx.open((1 << logn) - 1)] == M["xfe_trees"][str(logn)]["open_last"]
+    # arbitrary picklable leaves, non power of two counts (code/test_merkle.py:57-61)
+    for n in (1, 2, 3, 5, 13, 100):
+        e = M["blob_trees"][str(n)]
+        lv = blob_leaves(n)
+        tb = Merkle(lv)
+        assert tb.root().hex() == e["root"] and tb.depth == e["depth"]
+        assert [b.hex() for b in tb.open(0)] == e["open0"]
+        assert [b.hex() for b in tb.open(n - 1)] == e["open_last"]
+        assert hashlib.sha256(b"".join(tb.nodes[1:])).hexdigest() == e["nodes_sha256"]
+        assert all(Merkle.verify(tb.root(), i, tb.open(i), lv[i]) for i in range(n))
+    # non-canonical identity (a lifted element carries a foreign BaseField object): host pickling path
+    lifted = [env.xfield.lift(env.BaseFieldElement(i + 1, env.field)) for i in range(4)]
+    tl = Merkle(lifted)
+    assert tl.nodes[4] == hashlib.blake2b(pickle.dumps(lifted[0])).digest()
+    with pytest.raises(IndexError):
+        Merkle([]).root()
+
+
+def fri_input(env, logn, expansion, seed):
+    """make_golden.py fri_input: plain-int coset NTT of a random polynomial, canonical objects"""
+    from oracle import oracle as orc
+    from util import rand_xfe, root_of_unity
+    n = 1 << logn
+    coeffs = rand_xfe(seed, n // expansion)
+    planes = orc.coset_evaluate(7, root_of_unity(logn), coeffs, n)
+    return [X(env, *[int(planes[j][i]) for j in range(3)]) for i in range(n)], planes
+
+
+def run_fri_case(env, logn, expansion, s, seed, e):
+    n = 1 << logn
+    fri = env.Fri(env.field.generator(), env.field.primitive_nth_root(n), n, expansion, s, env.xfield)
+    cw, planes = fri_input(env, logn, expansion, seed)
+    assert xfe_digest(planes) == e["codeword_digest"]
+    ps = env.ProofStream()
+    top = fri.prove(cw, ps)
+    ser = ps.serialize()
+    assert top == e["top_level_indices"]
+    assert len(ps.objects) == e["num_objects"]
+    assert [o.hex() for o in ps.objects if isinstance(o, bytes)] == e["round_roots"]
+    assert len(ser) == e["transcript_len"]
+    assert hashlib.sha256(ser).hexdigest() == e["transcript_sha256"]
+    return fri, cw, ser
+
+
+def case_fri_transcripts(env, logs=(4, 5, 6, 8, 10)):
+    for logn in logs:
+        e = FS["gv6"][str(logn)]
+        fri, cw, ser = run_fri_case(env, logn, 4, 8, 200 + logn, e)
+        if logn <= 8:
+            assert fri.verify(env.ProofStream().deserialize(ser), env.Merkle(cw).root()) is True
+    run_fri_case(env, 12, 32, 40, 1312, FS["exp32_s40_12"])  # BASELINE config 4's "40 checks" needs expansion 32
+
+
+def case_test_fri_config(env):
+    """code/test_fri.py:5-59 with the transcript additionally pinned byte for byte"""
+    xfield, field = env.xfield, env.field
+    n = 1024
+    fri = env.Fri(field.generator(), field.primitive_nth_root(n), n, 16, 17, xfield)
+    polynomial = env.Polynomial([xfield(i) for i in range(64)])
+    codeword = fri.domain.xevaluate(polynomial)
+    e = FS["test_fri"]
+    assert xdig(codeword) == e["codeword_digest"]
+    root = env.Merkle(codeword).root()
+    assert root.hex() == e["root0"]
+    ps = env.ProofStream()
+    top = fri.prove(codeword, ps)
+    ser = ps.serialize()
+    assert top == e["top_level_indices"] and len(ps.objects) == e["num_objects"]
+    assert (len(ser), hashlib.sha256(ser).hexdigest()) == (e["transcript_len"], e["transcript_sha256"])
+    assert fri.verify(ps, root) is True
+    ps = env.ProofStream()
+    for i in range(0, 63 // 3):
+        codeword[i] = xfield.zero()  # in-place mutation of the same list object
+    fri.prove(codeword, ps)
+    assert not fri.verify(ps, [])
+
+
+def case_gv3(env):
+    R = random.Random(5)
+    n = 256
+    fri = env.Fri(env.field.generator(), env.field.primitive_nth_root(n), n, 4, 8, env.xfield)
+    poly = env.Polynomial([env.xfield.sample(bytes(R.getrandbits(8) for _ in range(30))) for _ in range(64)])
+    cw = fri.domain.xevaluate(poly, env.xfield)
+    e = FS["gv3"]
+    assert xdig(cw) == e["codeword_digest"]
+    ps = env.ProofStream()
+    assert fri.prove(cw, ps) == e["top_level_indices"]
+    ser = ps.serialize()
+    assert (len(ser), hashlib.sha256(ser).hexdigest()) == (e["transcript_len"], e["transcript_sha256"])
+
+
+def case_fri_errors(env):
+    f, xf = env.field, env.xfield
+    with pytest.raises(AssertionError):  # code/fri.py:69-72: 40 checks with expansion 4
+        fri = env.Fri(f.generator(), f.primitive_nth_root(64), 64, 4, 40, xf)
+        cw, _ = fri_input(env, 6, 4, 206)
+        fri.prove(cw, env.ProofStream())
+    with pytest.raises(AssertionError):  # code/fri.py:179-180
+        fri = env.Fri(f.generator(), f.primitive_nth_root(64), 64, 4, 8, xf)
+        fri.prove([xf.zero()] * 32, env.ProofStream())
+    with pytest.raises(AssertionError):  # code/fri.py:52
+        env.Fri(f.generator(), f.primitive_nth_root(4), 4, 4, 1, xf)
+    with pytest.raises(IndexError):  # single-round FRI: codewords[1] does not exist (code/fri.py:186-187)
+        fri = env.Fri(f.generator(), f.primitive_nth_root(8), 8, 4, 8, xf)
+        cw, _ = fri_input(env, 3, 4, 203)
+        fri.prove(cw, env.ProofStream())

@@ -1,0 +1,89 @@
+"""Host logic against the UNMODIFIED reference (authoring container only): the drop-in is installed
+over a host-memory test backend, then (a) every front-end case must reproduce the golden values,
+(b) the reference's own test files run unchanged, (c) uninstall() restores the originals."""
+import importlib
+import sys
+
+import pytest
+
+import frontend_cases as fc
+
+
+@pytest.fixture(scope="module")
+def env(reference_dropin):
+    mods = [importlib.import_module(m) for m in
+            ("algebra", "univariate", "extension_field", "ntt", "merkle", "ip", "fri")]
+    e = fc.make_env(*mods)
+    e.glue = reference_dropin
+    return e
+
+
+def test_patched_everywhere(env):
+    import fri
+    import ntt
+    assert ntt.ntt.__self__ is env.glue and fri.ntt.__self__ is env.glue  # star-imported copy rebound too
+    assert ntt.fast_multiply.__module__ == "ntt"  # untouched reference code riding on the patched ntt
+
+
+def test_ntt_golden(env):
+    fc.case_ntt_golden(env)
+
+
+def test_ntt_quirks(env):
+    fc.case_ntt_quirks(env)
+
+
+def test_coset_and_poly(env):
+    fc.case_coset_and_poly(env)
+
+
+def test_merkle(env):
+    fc.case_merkle(env)
+
+
+def test_fri_transcripts(env):
+    fc.case_fri_transcripts(env)
+
+
+def test_test_fri_config(env):
+    fc.case_test_fri_config(env)
+
+
+def test_gv3(env):
+    fc.case_gv3(env)
+
+
+def test_fri_errors(env):
+    fc.case_fri_errors(env)
+
+
+@pytest.mark.parametrize("modname,funcs", [
+    ("test_ntt", ["test_ntt", "test_intt", "test_multiply", "test_divide", "test_interpolate",
+                  "test_coset_evaluate", "test_batch_inverse"]),
+    ("test_merkle", ["test_merkle"]),
+    ("test_fri", ["test_fri"]),
+])
+def test_reference_own_tests_run_unmodified(env, modname, funcs, capsys):
+    """code/test_ntt.py, code/test_merkle.py, code/test_fri.py imported from the read-only checkout"""
+    launches0 = env.glue.engine.launch_count()
+    mod = importlib.import_module(modname)
+    for fn in funcs:
+        getattr(mod, fn)()
+    assert env.glue.engine.launch_count() > launches0  # they really went through the engine
+
+
+def test_uninstall_restores(reference_dropin):
+    from stark_brainfuck_b200 import dropin
+    import fri
+    import ntt
+    import univariate
+    glue = reference_dropin
+    eng = glue.engine
+    dropin.uninstall()
+    try:
+        assert ntt.ntt.__module__ == "ntt" and fri.ntt is ntt.ntt
+        assert univariate.Polynomial.scale.__qualname__ == "Polynomial.scale"
+        assert fri.Fri.prove.__qualname__ == "Fri.prove"
+    finally:
+        from conftest import REFERENCE_DIR
+        dropin.install(REFERENCE_DIR, engine=eng)
