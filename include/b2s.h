@@ -144,6 +144,21 @@ int b2s_fri_fold(const uint64_t *d_cw, uint64_t cw_stride, uint64_t N, const uin
 int b2s_gather(const uint64_t *d_planes, uint64_t plane_stride, uint32_t n_planes, const uint64_t *h_indices,
                uint32_t n_indices, uint64_t *h_out, void *stream);
 
+/* ---- multi-GPU exchange step of the four-step NTT (no counterpart in the single-process
+ * reference) ------------------------------------------------------------
+ * n = n1*n2, j = j1 + n1*j2.  The caller owns `rows` = n1/G columns j1 (first one: row_base) as
+ * planes d_in[j1_local][k2] (after the local length-n2 transforms, cols = n2).  Writes
+ *     out_ptrs[k2 / (cols/n_peers)][(k2 % (cols/n_peers)) * out_row_stride + out_col_offset + j1_local]
+ *         = in[j1_local][k2] * omega^(tw_mul * j1 * k2)
+ * i.e. twiddle + transpose + placement in one kernel.  out_ptrs are device pointers: slices of a
+ * local send buffer (NCCL all-to-all follows) or peer buffers mapped over NVLink (the kernel
+ * then IS the exchange).  out_ptrs itself is a HOST array of n_peers <= 16 pointers. */
+int b2s_dist_twiddle_transpose(const uint64_t *d_in, uint64_t in_stride, uint32_t rows, uint32_t cols,
+                               uint64_t row_base, uint64_t omega, uint64_t tw_mul, uint64_t *const *out_ptrs,
+                               uint32_t n_peers, uint64_t out_row_stride, uint64_t out_col_offset, void *stream);
+/* d_out[b][a][0..C) = d_in[a][b][0..C): reorders the blocks received by an all-to-all. */
+int b2s_block_permute(const uint64_t *d_in, uint64_t *d_out, uint32_t A, uint32_t B, uint32_t C, void *stream);
+
 /* ---- timing helper -----------------------------------------------------------------
  * Runs b2s_ntt `iters` times back to back on `stream` bracketed by CUDA events and
  * returns the mean milliseconds per call in *ms (used by bench.py for the roofline of the

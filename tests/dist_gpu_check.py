@@ -1,0 +1,75 @@
+"""Multi-GPU parity + timing of the sharded four-step NTT.  Launch (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_gpu_check.py [--log-n 20] [--exchange nccl,p2p]
+Rank 0 gathers the shards, compares with the CPU oracle bit for bit and prints one JSON line."""
+import argparse
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--exchange", default="nccl,p2p")
+    ap.add_argument("--iters", type=int, default=20)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from oracle import oracle as orc
+    from stark_brainfuck_b200 import Engine
+    from stark_brainfuck_b200.dist import DistNTT, assemble_output, scatter_columns
+    from util import rand_bfe, root_of_unity
+    eng = Engine(local)
+    log_n = args.log_n
+    log_n1 = log_n // 2
+    x = rand_bfe(7000 + log_n, 1 << log_n)
+    w = root_of_unity(log_n)
+    ref = orc.ntt(w, x) if rank == 0 else None
+    report = {"n_gpus": world, "log_n": log_n}
+    for ex in args.exchange.split(","):
+        try:
+            d = DistNTT(eng, exchange=ex)
+            loc = eng.upload(scatter_columns(x, log_n, log_n1, rank, world))
+            out = d.transform(loc, log_n, w, log_n1=log_n1)
+            back = d.transform(out, log_n, w, inverse=True, log_n1=log_n - log_n1)
+            torch.cuda.synchronize()
+            ok_rt = bool(torch.equal(back, loc))
+            parts = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(parts, out)
+            ok = None
+            if rank == 0:
+                got = assemble_output([eng.download(p) for p in parts], log_n, log_n1)
+                ok = bool(np.array_equal(got, ref))
+            # timing: device events, max over ranks
+            for _ in range(3):
+                d.transform(loc, log_n, w, log_n1=log_n1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                d.transform(loc, log_n, w, log_n1=log_n1)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / args.iters], device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            report[ex] = {"matches_oracle": ok, "roundtrip_exact": ok_rt, "ms_per_transform": float(t[0])}
+        except Exception as e:  # report, do not hang the other ranks
+            report[ex] = {"error": repr(e)[:300]}
+    if rank == 0:
+        print(json.dumps(report))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -145,6 +145,27 @@ class FakeLib:
         return 0
 
 
+    def b2s_dist_twiddle_transpose(self, d_in, in_stride, rows, cols, row_base, omega, tw_mul, out_ptrs, n_peers,
+                                   out_row_stride, out_col_offset, stream):
+        self.launches += 1
+        P = orc.P
+        cpp = cols // n_peers
+        for r in range(rows):
+            row = _u64(_addr(d_in) + 8 * in_stride * r, cols)
+            j1 = row_base + r
+            for c in range(cols):
+                v = int(row[c]) * pow(omega, tw_mul * j1 * c, P) % P
+                dst = _u64(_addr(out_ptrs[c // cpp]) + 8 * ((c % cpp) * out_row_stride + out_col_offset + r), 1)
+                dst[0] = v
+        return 0
+
+    def b2s_block_permute(self, d_in, d_out, A, B, Cn, stream):
+        self.launches += 1
+        src = _u64(_addr(d_in), A * B * Cn).reshape(A, B, Cn)
+        _u64(_addr(d_out), A * B * Cn).reshape(B, A, Cn)[:] = src.transpose(1, 0, 2)
+        return 0
+
+
 def fake_engine():
     from stark_brainfuck_b200 import Engine
     return Engine(lib=FakeLib(), device="cpu")

@@ -1,0 +1,26 @@
+"""Multi-GPU parity (needs >= 2 visible GPUs; skipped otherwise): launches tests/dist_gpu_check.py
+under torchrun and checks the sharded NTT against the oracle for both exchange variants."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_sharded_ntt_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(HERE, "dist_gpu_check.py"), "--log-n", "16",
+           "--iters", "3"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rep = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert rep["nccl"]["matches_oracle"] is True and rep["nccl"]["roundtrip_exact"] is True
+    if "error" not in rep.get("p2p", {"error": 1}):
+        assert rep["p2p"]["matches_oracle"] is True and rep["p2p"]["roundtrip_exact"] is True
