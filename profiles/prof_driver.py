@@ -24,6 +24,16 @@ if what in ("all", "ntt"):
     yb = eng.empty(32, n)
     for _ in range(2):
         eng.ntt(xb, logn, w, offset=7, out=yb)
+if what.startswith("nttb"):  # batched transform of another size: nttb16 -> 2^16 x 512 planes (same total work as 32 x 2^20)
+    lg = int(what[4:])
+    q = (32 << 20) >> lg
+    wl = root_of_unity(lg)
+    xb = torch.randint(0, 2 ** 62, (q, 1 << lg), dtype=torch.int64, device=eng.device)
+    yb = eng.empty(q, 1 << lg)
+    for _ in range(3):
+        eng.ntt(xb, lg, wl, offset=7, out=yb)
+    ms, _ = eng.ntt_timed(xb, lg, wl, offset=7, out=yb, iters=5)
+    print("batched 2^%d x %d planes: %.3f ms" % (lg, q, ms))
 if what in ("all", "fri"):
     mirror.register()
     tpl = mirror.binding.xfe_templates(mirror.xfield)

@@ -1,0 +1,283 @@
+// ntt4.cuh -- one PASS of the batched NTT (replaces the radix-2 recursion of code/ntt.py:4-23 for
+// one digit of the index; the plan over passes lives in ntt4_plan.h / ntt.cu).
+//
+// A pass computes, for every column of its tile, the R-point transform over the rows
+//     X[k] = sum_r x[r] * w_R^(r k),      R = 2^t * 16^a,  t = 0..3,  a = 1..2
+// Design constraint that shaped it (profiles/microbench/icache.cu): an SM streams
+// code that each warp executes once at ~1.5 B/clk, so a fully unrolled pass (100 KB of SASS) is
+// bound by instruction fetch.  Here the executed code is three small loop bodies (~25 KB):
+//   tail   global -> registers -> 2^t-point transform over the top digit -> * w_R^(low*k) ->
+//          shared memory               (fused: zero padding, row part of the coset scale)
+//   core   `a` times: shared -> registers -> 16-point transform (DIT, twiddles from the
+//          kernel-parameter constant bank) -> * w^(lo*k) -> shared, in place
+//   out    shared -> * inter-pass twiddle w^(col*k) (four interleaved running products per
+//          thread) | * n^-1 offset^-k | canonicalise -> global
+// The tile lives in shared memory as [col][row] with one pad element per 16 rows and a column
+// stride = 4 (mod 16) elements, which makes every 64-bit access pattern of the three phases
+// conflict-free (DESIGN.md has the lane -> bank tables).
+// All multiplications are Montgomery multiplications by canonical table values (glmont.cuh).
+// The phase functions are __host__ __device__: tests/ntt4_hostcheck.cpp runs them thread by
+// thread on the CPU against the oracle.
+#pragma once
+#include "glmont.cuh"
+
+enum : u32 {
+    P4_FIRST = 1,    // bounds check against n_in (zero padding)
+    P4_OUT_MUL = 2,  // last pass: multiply the output by out_mul (n^-1)
+    P4_LAST = 4,     // last pass of the plan: rows are the contiguous input dimension
+};
+
+struct Pass4Params {
+    const u64 *in;
+    u64 *out;
+    u64 in_plane_stride, out_plane_stride;
+    u64 in_blk_stride, out_blk_stride;
+    u64 in_row_stride, in_col_stride, out_row_stride;  // output columns are always contiguous
+    const u64 *tw_tail;    // [k][low]: w_R^(k*low), k < 2^t, low < R/2^t          (null when t == 0)
+    const u64 *tw_core;    // [k][lo]:  w_256^(k*lo), k < 16, lo < 16               (a == 2 only)
+    const u64 *in_scale;   // (scale^in_row_stride)^row, row < R, or null
+    const u64 *out_scale;  // (scale^out_row_stride)^k, k < R, or null      (last pass, inverse coset)
+    const u64 *tw_lo;      // W^i, i < 1024, W = omega^tw_mul                 (non-last passes)
+    const u64 *tw_hi;      // W^(1024 i)
+    const u64 *col_scale;  // scale^col, col < number of columns, or null    (first pass, forward coset)
+    u64 out_mul;           // n^-1
+    u64 n_in;
+    u32 flags;
+    u32 log_R, log_T, a;  // R = 2^log_R rows, T = 2^log_T columns per tile, a core steps (t = log_R - 4a)
+    u32 cs;               // shared-memory column stride (elements)
+    u64 s_sq[32];         // scale^(2^b)
+    u64 w16[8];           // z^e, e < 8, z a primitive 16th root with z^(16/M) = w_M (M = 2, 4, 8, 16)
+    // all table entries and out_mul, s_sq, w16 are in Montgomery form (glmont.cuh)
+};
+
+GL_HD constexpr int bitrev4_c(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+GL_HD u64 canon4(u64 x) {
+#if defined(__CUDA_ARCH__)
+    u32 x0, x1, r0, r1;
+    m_unpack(x, x0, x1);
+    // x >= p  <=>  x1 == 0xFFFFFFFF and x0 != 0,  and then x - p = x0 - 1
+    asm("{\n .reg .pred q;\n"
+        " setp.eq.u32     q, %3, 0xFFFFFFFF;\n"
+        " setp.ne.and.u32 q, %2, 0, q;\n"
+        " mov.u32         %0, %2;\n"
+        " @q add.u32      %0, %2, 0xFFFFFFFF;\n"
+        " selp.u32        %1, 0, %3, q;\n}"
+        : "=&r"(r0), "=r"(r1)
+        : "r"(x0), "r"(x1));
+    return m_pack(r0, r1);
+#else
+    return lcanon(x);
+#endif
+}
+
+// In-register M-point transform, decimation in time.  On entry v[j] = x[bitrev(j)], all
+// canonical; on exit v[k] = X[k] (lazy).  w[e * ws] = w_M^e in Montgomery form, e < M/2.
+// One flat loop of M/2 butterflies per stage with compile-time bounds: every index into v
+// (registers) and w (constant bank) is a literal after unrolling.
+template <int LOG_M, int S>
+GL_HD void dit4_stage(u64 (&v)[1 << LOG_M], const u64 *w, const int ws) {
+    constexpr int M = 1 << LOG_M, half = 1 << (S - 1);
+#pragma unroll
+    for (int i = 0; i < M / 2; ++i) {
+        const int j = i & (half - 1);
+        const int lo = ((i >> (S - 1)) << S) + j, hi = lo + half;
+        const u64 u = v[lo];
+        u64 t = v[hi];
+        if (j == 0) {
+            if (S > 1) t = canon4(t);
+        } else {
+            t = mont_mul(t, w[(j << (LOG_M - S)) * ws]);
+        }
+        v[lo] = ladd(u, t);
+        v[hi] = lsub(u, t);
+    }
+}
+template <int LOG_M, int S = 1>
+GL_HD void dft4_dit(u64 (&v)[1 << LOG_M], const u64 *w, const int ws) {
+    if constexpr (S <= LOG_M) {
+        dit4_stage<LOG_M, S>(v, w, ws);
+        dft4_dit<LOG_M, S + 1>(v, w, ws);
+    }
+}
+
+GL_HD u64 mont_pow_sq4(const u64 *sq, u64 e) {
+    u64 acc = GL_EPS;  // 1 in Montgomery form
+    for (int b = 0; e; ++b, e >>= 1)
+        if (e & 1) acc = mont_mul(acc, sq[b]);
+    return acc;
+}
+
+// shared-memory index of (col, row): one pad element per 16 rows, column stride cs
+GL_HD u32 sidx4(u32 col, u32 row, u32 cs) { return col * cs + row + (row >> 4); }
+
+// column stride = 16/T (mod 16) elements for tiles of T = 2 or 4 columns: a 64-bit wavefront
+// (16 lanes = T columns x 16/T consecutive rows) then falls into 16 distinct bank pairs
+static inline u32 pass4_cs(u32 log_R, u32 log_T) {
+    const u32 rows = (1u << log_R) + ((1u << log_R) >> 4);
+    if (log_T == 0) return rows;
+    const u32 want = 16u >> log_T;
+    return rows + ((want + 16 - rows % 16) % 16);
+}
+static inline u32 pass4_threads(u32 log_R, u32 log_T) {
+    const u32 nt = (1u << (log_R + log_T)) >> 4;
+    return nt < 32 ? 32 : nt;
+}
+static inline size_t pass4_smem_elems(u32 log_R, u32 log_T) { return (size_t)pass4_cs(log_R, log_T) << log_T; }
+
+// ---- tail: global -> 2^t-point transform over the top digit -> twiddle -> shared --------------
+// `tables_ready()` blocks until the staged tables can be read (device: mbarrier wait; host: no-op);
+// it is called after the global loads have been issued.  Index arithmetic is 32-bit (a plane has
+// at most 2^30 elements) and strength-reduced: element j of a group sits j' * L rows further.
+template <int TL, class Ready>
+GL_HD void pass4_tail(const Pass4Params &P, const u32 tid, const u32 nthreads, const u32 bx, const u32 by,
+                      const u32 bz, const u64 *tw_tail_s, u64 *S, Ready tables_ready) {
+    constexpr int M = 1 << TL;
+    const u32 log_L = P.log_R - TL, L = 1u << log_L;  // rows per value of the top digit (>= 16)
+    const u32 T = 1u << P.log_T;
+    const u32 ngroups = L << P.log_T;
+    const bool rowfast = (P.flags & P4_LAST) && P.log_T > 0;
+    const bool check = (P.flags & P4_FIRST) != 0;
+    const u32 n_in = (u32)P.n_in, rs = (u32)P.in_row_stride, cst = (u32)P.in_col_stride;
+    const u32 Lrs = L * rs;           // global distance between consecutive values of the top digit
+    const u32 Lp = L + (L >> 4);      // the same in (padded) shared memory
+    const u32 blk0 = by * (u32)P.in_blk_stride + (bx << P.log_T) * cst;
+    const u64 *plane0 = P.in + (u64)bz * P.in_plane_stride;
+#pragma unroll 1
+    for (u32 g = tid; g < ngroups; g += nthreads) {
+        u32 col, low;
+        if (rowfast) {  // rows are the contiguous global dimension: lanes run along the rows
+            low = g & (L - 1);
+            col = g >> log_L;
+        } else {
+            col = g & (T - 1);
+            low = g >> P.log_T;
+        }
+        const u32 idx0 = blk0 + col * cst + low * rs;
+        u64 v[M];
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+            const u32 idx = idx0 + (u32)bitrev4_c(j, TL) * Lrs;
+            const bool ok = !check || idx < n_in;
+            const u64 x = plane0[ok ? idx : 0];  // n_in == 0 never launches
+            v[j] = ok ? x : 0;
+        }
+        if (P.in_scale) {
+#pragma unroll
+            for (int j = 0; j < M; ++j) v[j] = mont_mul(v[j], P.in_scale[(u32)bitrev4_c(j, TL) * L + low]);
+        }
+        if (TL > 0) {
+            dft4_dit<TL>(v, P.w16, 16 >> TL);
+            v[0] = canon4(v[0]);
+            if (g == tid) tables_ready();
+#pragma unroll
+            for (int k = 1; k < M; ++k) v[k] = mont_mul(v[k], tw_tail_s[(u32)k * L + low]);
+        }
+        u64 *dst = S + col * P.cs + low + (low >> 4);
+#pragma unroll
+        for (int k = 0; k < M; ++k) dst[(u32)k * Lp] = v[k];
+    }
+    if (TL == 0 || tid >= ngroups) tables_ready();  // every thread passes the wait exactly once
+}
+
+// ---- core: one in-place 16-point step over the digit of weight L = 16^(a-1-s) -------------------
+GL_HD void pass4_core(const Pass4Params &P, const u32 s, const u32 tid, const u32 nthreads, const u64 *tw_core_s,
+                      u64 *S) {
+    const u32 log_L = 4 * (P.a - 1 - s), L = 1u << log_L;
+    const u32 Lp = L + (L >> 4);  // padded distance between consecutive digit values (L = 1 or a multiple of 16)
+    const u32 T = 1u << P.log_T;
+    const u32 ngroups = (1u << (P.log_R + P.log_T)) >> 4;
+#pragma unroll 1
+    for (u32 g = tid; g < ngroups; g += nthreads) {
+        const u32 col = g & (T - 1);
+        const u32 q = g >> P.log_T;
+        const u32 lo = q & (L - 1), hi = q >> log_L;
+        const u32 row0 = ((hi << 4) << log_L) + lo;
+        u64 *base = S + col * P.cs + row0 + (row0 >> 4);
+        u64 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = base[(u32)bitrev4_c(j, 4) * Lp];
+        dft4_dit<4>(v, P.w16, 1);
+        if (log_L > 0) {  // not the last step: twiddle w_(16 L)^(lo k); products are canonical
+            v[0] = canon4(v[0]);
+#pragma unroll
+            for (int k = 1; k < 16; ++k) v[k] = mont_mul(v[k], tw_core_s[((u32)k << log_L) + lo]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) base[(u32)k * Lp] = v[k];
+    }
+}
+
+// ---- out: shared -> output scaling -> global -------------------------------------------------------
+// Thread (col, hi) owns the 16 positions hi*16 + i it wrote in the last core step; they hold
+// X[k], k = krev(hi) + (R/16) i, an arithmetic progression, so the inter-pass twiddle
+// W^(colg k) is a running product.
+GL_HD void pass4_out(const Pass4Params &P, const u32 tid, const u32 nthreads, const u32 bx, const u32 by, const u32 bz,
+                     const u64 *S) {
+    const u32 T = 1u << P.log_T;
+    const u32 ngroups = (1u << (P.log_R + P.log_T)) >> 4;
+    const u32 t = P.log_R - 4 * P.a;
+    const bool last = (P.flags & P4_LAST) != 0;
+    const u32 log_h = 4 * (P.a - 1);
+    const u32 log_kstride = P.log_R - 4;
+    const u64 ostep = P.out_row_stride << log_kstride;  // global distance between consecutive i
+#pragma unroll 1
+    for (u32 g = tid; g < ngroups; g += nthreads) {
+        const u32 col = g & (T - 1);
+        const u32 hi = g >> P.log_T;
+        // position hi*16 + i  <->  k = kT + 2^t * (k1 + 16^(a-1) * i),  hi = kT * 16^(a-1) + k1
+        const u32 k1 = hi & ((1u << log_h) - 1), kT = hi >> log_h;
+        const u32 kbase = kT + (k1 << t);
+        const u32 colg = (bx << P.log_T) + col;
+        u64 *out = P.out + (u64)bz * P.out_plane_stride + (u64)by * P.out_blk_stride + colg +
+                   (u64)kbase * P.out_row_stride;
+        const u64 *src = S + col * P.cs + hi * 17;  // rows hi*16 .. hi*16+15: no pad inside
+        if (!last) {
+            // X[k] * W^(colg k) (* scale^colg): c[j] runs over k = kbase + kstride * (4 i + j)
+            const u64 e0 = (u64)colg * kbase, e1 = (u64)colg << log_kstride;
+            u64 c0 = mont_mul(P.tw_lo[e0 & 1023], P.tw_hi[e0 >> 10]);
+            if (P.col_scale) c0 = mont_mul(c0, P.col_scale[colg]);
+            const u64 step1 = mont_mul(P.tw_lo[e1 & 1023], P.tw_hi[e1 >> 10]);
+            const u64 step2 = mont_mul(step1, step1);
+            const u64 step4 = mont_mul(step2, step2);
+            u64 c[4];
+            c[0] = c0;
+            c[1] = mont_mul(c0, step1);
+            c[2] = mont_mul(c0, step2);
+            c[3] = mont_mul(c[1], step2);
+#pragma unroll 1
+            for (u32 i = 0; i < 4; ++i) {
+#pragma unroll
+                for (u32 j = 0; j < 4; ++j) {
+                    out[0] = mont_mul(src[4 * i + j], c[j]);
+                    out += ostep;
+                    c[j] = mont_mul(c[j], step4);
+                }
+            }
+        } else if (P.out_scale) {
+            const u64 cc = mont_mul(P.out_mul, mont_pow_sq4(P.s_sq, (u64)by * P.out_blk_stride + colg));
+            const u64 *os = P.out_scale + kbase;
+#pragma unroll 1
+            for (u32 i = 0; i < 16; ++i) {
+                out[0] = mont_mul(mont_mul(src[i], cc), os[(u64)i << log_kstride]);
+                out += ostep;
+            }
+        } else if (P.flags & P4_OUT_MUL) {
+#pragma unroll 4
+            for (u32 i = 0; i < 16; ++i) {
+                out[0] = mont_mul(src[i], P.out_mul);
+                out += ostep;
+            }
+        } else {
+#pragma unroll 4
+            for (u32 i = 0; i < 16; ++i) {
+                out[0] = canon4(src[i]);
+                out += ostep;
+            }
+        }
+    }
+}
