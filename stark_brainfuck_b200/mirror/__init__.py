@@ -11,10 +11,30 @@ names: register() installs them in sys.modules (refusing to shadow a loaded refe
 unregister() removes them.
 """
 import sys
+import types
 
-from . import algebra, extension_field, fri, ip, merkle, ntt, univariate
+from . import fri, hostmodel, merkle, ntt
 from ..glue import Glue
 from ..marshal import Binding
+
+
+def _module(name, exported):
+    """a module object that exposes `exported` names of hostmodel (what `from X import *` of the
+    reference's module X would bring in, including what X itself star-imported)"""
+    mod = types.ModuleType(name, "stark_brainfuck_b200.mirror view of the reference's `%s` module" % name)
+    mod.__file__ = hostmodel.__file__
+    for n in exported:
+        setattr(mod, n, getattr(hostmodel, n))
+    return mod
+
+
+_ALGEBRA = ("P", "xgcd", "BaseFieldElement", "BaseField")
+_UNIVARIATE = _ALGEBRA + ("Polynomial", "test_colinearity")
+_EXTENSION = _UNIVARIATE + ("ExtensionFieldElement", "ExtensionField")
+algebra = _module("algebra", _ALGEBRA)
+univariate = _module("univariate", _UNIVARIATE)
+extension_field = _module("extension_field", _EXTENSION)
+ip = _module("ip", ("ProofStream", "pickle", "shake_256"))
 
 NAMES = ("algebra", "univariate", "extension_field", "ntt", "merkle", "ip", "fri")
 _MODS = {"algebra": algebra, "univariate": univariate, "extension_field": extension_field, "ntt": ntt,

@@ -3,12 +3,9 @@ Domain.  Prover-side work (Domain.evaluate/xevaluate/interpolate/xinterpolate, c
 query_last, prove) runs on the device through the glue; verify is the host-side checker."""
 from hashlib import blake2b
 
-from .algebra import *  # noqa: F401,F403
-from .extension_field import ExtensionField, ExtensionFieldElement  # noqa: F401
-from .ip import *  # noqa: F401,F403
+from .hostmodel import *  # noqa: F401,F403  (the classes of algebra / univariate / extension_field / ip)
 from .merkle import *  # noqa: F401,F403
 from .ntt import *  # noqa: F401,F403
-from .univariate import *  # noqa: F401,F403
 
 
 def _g():
@@ -87,64 +84,65 @@ class Fri:
     def prove(self, codeword, proof_stream):
         return _g().fri_prove(self, codeword, proof_stream)
 
-    def verify(self, proof_stream, root):
-        """code/fri.py:201-319.  Host-side; returns False (after printing why) on rejection."""
-        xf = self.field
-        omega, offset = xf.lift(self.domain.omega), xf.lift(self.domain.offset)
-        rounds = self.num_rounds()
+    # ---- verifier (host side; the acceptance check of code/fri.py:201-319) -----------------
+    def _read_commitments(self, proof_stream, root):
+        """Merkle roots of all rounds and the folding challenges re-derived from the transcript."""
         roots, alphas = [root], []
-        for r in range(rounds):
-            if r > 0:
+        for r in range(self.num_rounds()):
+            if r:
                 roots.append(proof_stream.pull())
-            alphas.append(xf.sample(proof_stream.verifier_fiat_shamir()))
-        last_codeword = proof_stream.pull()
-        if roots[-1] != Merkle(last_codeword).root():
+            alphas.append(self.field.sample(proof_stream.verifier_fiat_shamir()))
+        return roots, alphas
+
+    def _last_codeword_ok(self, last_codeword, last_root, omega, offset):
+        """the final codeword matches its root and has degree < length / expansion_factor"""
+        if last_root != Merkle(last_codeword).root():
             print("last codeword is not well formed")
             return False
-        max_degree = len(last_codeword) // self.expansion_factor - 1
-        last_omega, last_offset = omega, offset
-        for _ in range(rounds - 1):
-            last_omega, last_offset = last_omega ^ 2, last_offset ^ 2
-        assert last_omega.inverse() == last_omega ^ (len(last_codeword) - 1), "omega does not have right order"
-        last_domain = [last_offset * (last_omega ^ i) for i in range(len(last_codeword))]
-        poly = Polynomial.interpolate_domain(last_domain, last_codeword)
-        assert poly.evaluate_domain(last_domain) == last_codeword, "re-evaluated codeword does not match original!"
-        if poly.degree() > max_degree:
+        assert omega.inverse() == omega ^ (len(last_codeword) - 1), "omega does not have right order"
+        points = [offset * (omega ^ i) for i in range(len(last_codeword))]
+        poly = Polynomial.interpolate_domain(points, last_codeword)
+        assert poly.evaluate_domain(points) == last_codeword, "re-evaluated codeword does not match original!"
+        return poly.degree() <= len(last_codeword) // self.expansion_factor - 1
+
+    def _layer_ok(self, proof_stream, this_root, next_root, alpha, omega, offset, c_idx, half, last_codeword):
+        """colinearity of the s opened triples of one layer and their authentication paths;
+        next_root is None on the final layer, whose c values are read off the last codeword"""
+        triples = [proof_stream.pull() for _ in c_idx]
+        for c, (ay, by, cy) in zip(c_idx, triples):
+            ax, bx = offset * (omega ^ c), offset * (omega ^ (c + half))
+            if not test_colinearity([(ax, ay), (bx, by), (alpha, cy)]):
+                print("colinearity check failure")
+                return False
+        for c, (ay, by, cy) in zip(c_idx, triples):
+            checks = [("aa", this_root, c, ay), ("bb", this_root, c + half, by)]
+            if next_root is not None:
+                checks.append(("cc", next_root, c, cy))
+            for label, tree_root, index, leaf in checks:
+                if not Merkle.verify(tree_root, index, proof_stream.pull(), leaf):
+                    print("merkle authentication path verification fails for " + label)
+                    return False
+        if next_root is None and any(cy != last_codeword[c] for c, (_, _, cy) in zip(c_idx, triples)):
+            print("leafs in last round do not correspond to last codeword")
             return False
-        n = self.domain.length
+        return True
+
+    def verify(self, proof_stream, root):
+        """Returns False (after printing why) on rejection."""
+        rounds, n = self.num_rounds(), self.domain.length
+        omega, offset = self.field.lift(self.domain.omega), self.field.lift(self.domain.offset)
+        roots, alphas = self._read_commitments(proof_stream, root)
+        last_codeword = proof_stream.pull()
+        squarings = 1 << (rounds - 1)
+        if not self._last_codeword_ok(last_codeword, roots[-1], omega ^ squarings, offset ^ squarings):
+            return False
         top = self.sample_indices(proof_stream.verifier_fiat_shamir(), n >> 1, n >> (rounds - 1),
                                   self.num_colinearity_tests)
-        s = self.num_colinearity_tests
         for r in range(rounds - 1):
             half = n >> (r + 1)
-            c_idx = [i % half for i in top]
-            a_idx = list(c_idx)
-            b_idx = [i + half for i in a_idx]
-            aa, bb, cc = [], [], []
-            for k in range(s):
-                ay, by, cy = proof_stream.pull()
-                aa.append(ay)
-                bb.append(by)
-                cc.append(cy)
-                ax, bx = offset * (omega ^ a_idx[k]), offset * (omega ^ b_idx[k])
-                if not test_colinearity([(ax, ay), (bx, by), (alphas[r], cy)]):
-                    print("colinearity check failure")
-                    return False
-            for k in range(s):
-                if not Merkle.verify(roots[r], a_idx[k], proof_stream.pull(), aa[k]):
-                    print("merkle authentication path verification fails for aa")
-                    return False
-                if not Merkle.verify(roots[r], b_idx[k], proof_stream.pull(), bb[k]):
-                    print("merkle authentication path verification fails for bb")
-                    return False
-                if r + 1 != rounds - 1:
-                    if not Merkle.verify(roots[r + 1], c_idx[k], proof_stream.pull(), cc[k]):
-                        print("merkle authentication path verification fails for cc")
-                        return False
-            if r + 1 == rounds - 1:
-                for k in range(s):
-                    if cc[k] != last_codeword[c_idx[k]]:
-                        print("leafs in last round do not correspond to last codeword")
-                        return False
+            final = r + 2 == rounds
+            if not self._layer_ok(proof_stream, roots[r], None if final else roots[r + 1], alphas[r], omega, offset,
+                                  [i % half for i in top], half, last_codeword):
+                return False
             omega, offset = omega ^ 2, offset ^ 2
         return True

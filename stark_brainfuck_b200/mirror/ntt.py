@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's `ntt` module (code/ntt.py).  ntt / intt /
 fast_coset_evaluate / fast_coset_interpolate run on the device; the remaining fast
 polynomial routines are the reference's divide-and-conquer compositions of those."""
-from .univariate import *  # noqa: F401,F403
+from .hostmodel import *  # noqa: F401,F403
 
 
 def _g():
