@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 LOG_N = 20
+P_MOD = 18446744069414584321
 METRIC = "ntt_field_mul_per_s"
 UNIT = "field-mul/s"
 
@@ -244,6 +245,37 @@ def run_b200(args):
         extra["batched_32_planes_hbm_gbs"] = 16.0 * n * q / (ms_b / 1e3) / 1e9
     except Exception as e:  # informational only
         extra["batched_error"] = str(e)
+    # ---- extra: the Merkle / FRI half of the path at a 2^20 domain (BASELINE configs[3] with SURVEY D8's
+    # fix), device side: round-0 tree, then fold + next tree per round with fixed challenges ------------
+    try:
+        if rank == 0:
+            from stark_brainfuck_b200 import mirror
+            mirror.register()
+            tpl = mirror.binding.xfe_templates(mirror.xfield)
+            rng = np.random.default_rng(5)
+            cw0 = eng.upload(rng.integers(0, P_MOD, size=(3, n), dtype=np.uint64, endpoint=False))
+            best = None
+            for _ in range(4):
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                eng.merkle_field(cw0, tpl)
+                e1.record()
+                cw, N, ww, off = cw0, n, w, 7
+                while N // 2 > 4:
+                    cw, _nodes = eng.fri_fold(cw, [3, 5, 7], off, ww, tpl)
+                    N //= 2
+                    ww, off = ww * ww % P_MOD, off * off % P_MOD
+                e2.record()
+                torch.cuda.synchronize(dev)
+                t = (e0.elapsed_time(e1), e0.elapsed_time(e2))
+                best = t if best is None or t[1] < best[1] else best
+            extra["merkle_2p20_xfe_leaves_ms"] = best[0]
+            extra["merkle_2p20_hbm_gbs"] = 152.0 * n / (best[0] / 1e3) / 1e9
+            extra["fri_commit_2p20_expansion4_ms"] = best[1]
+            extra["fri_commit_2p20_hbm_gbs"] = 328.0 * n / (best[1] / 1e3) / 1e9
+            mirror.unregister()
+    except Exception as e:  # informational only
+        extra["fri_error"] = str(e)
 
     if rank != 0:
         if world > 1:

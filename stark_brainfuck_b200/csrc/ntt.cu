@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(512, 2) ntt4_pass_kernel(const __grid_constant
                          : "memory");
     }
     __syncthreads();  // mbarrier initialised
+    // Programmatic dependent launch: a non-first pass is launched while its predecessor drains;
+    // everything above (and the launch latency) overlaps it, the data it reads does not.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     auto tables_ready = [mbar_a] {
         asm volatile(
             "{\n"
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(512, 2) ntt4_pass_kernel(const __grid_constant
         pass4_core(P, s, tid, nthreads, tw_core_s, S);
         if (s + 1 < P.a) __syncthreads();
     }
+    asm volatile("griddepcontrol.launch_dependents;");
     // the out phase reads back exactly what this thread wrote in the last core step
     pass4_out(P, tid, nthreads, blockIdx.x, blockIdx.y, blockIdx.z, S);
 }
@@ -159,7 +163,17 @@ int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
         B2S_CUDA(cudaFuncSetAttribute(ntt4_pass_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = smem;
     }
-    ntt4_pass_kernel<TL><<<dim3(pl.grid_x, pl.grid_y, n_planes), pass4_threads(P.log_R, P.log_T), smem, st>>>(P);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid_x, pl.grid_y, n_planes);
+    cfg.blockDim = dim3(pass4_threads(P.log_R, P.log_T));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pl.first ? 0 : 1;  // the first pass depends on whatever the caller enqueued before
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, ntt4_pass_kernel<TL>, P));
     B2S_LAUNCHED();
     return 0;
 }

@@ -147,8 +147,13 @@ GL_HD void pass4_tail(const Pass4Params &P, const u32 tid, const u32 nthreads, c
     const u32 Lp = L + (L >> 4);      // the same in (padded) shared memory
     const u32 blk0 = by * (u32)P.in_blk_stride + (bx << P.log_T) * cst;
     const u64 *plane0 = P.in + (u64)bz * P.in_plane_stride;
-#pragma unroll 1
-    for (u32 g = tid; g < ngroups; g += nthreads) {
+    // A thread owns NG = 16 / M groups (g = tid + i * nthreads).  All 16 loads are issued before any
+    // arithmetic, so a pass pays one global-memory round trip, not NG of them.
+    constexpr int NG = 16 >> TL;
+    u64 v[NG][M];
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        const u32 g = tid + (u32)gi * nthreads;
         u32 col, low;
         if (rowfast) {  // rows are the contiguous global dimension: lanes run along the rows
             low = g & (L - 1);
@@ -158,30 +163,48 @@ GL_HD void pass4_tail(const Pass4Params &P, const u32 tid, const u32 nthreads, c
             low = g >> P.log_T;
         }
         const u32 idx0 = blk0 + col * cst + low * rs;
-        u64 v[M];
 #pragma unroll
         for (int j = 0; j < M; ++j) {
             const u32 idx = idx0 + (u32)bitrev4_c(j, TL) * Lrs;
-            const bool ok = !check || idx < n_in;
+            const bool ok = g < ngroups && (!check || idx < n_in);
             const u64 x = plane0[ok ? idx : 0];  // n_in == 0 never launches
-            v[j] = ok ? x : 0;
+            v[gi][j] = ok ? x : 0;
         }
-        if (P.in_scale) {
-#pragma unroll
-            for (int j = 0; j < M; ++j) v[j] = mont_mul(v[j], P.in_scale[(u32)bitrev4_c(j, TL) * L + low]);
-        }
-        if (TL > 0) {
-            dft4_dit<TL>(v, P.w16, 16 >> TL);
-            v[0] = canon4(v[0]);
-            if (g == tid) tables_ready();
-#pragma unroll
-            for (int k = 1; k < M; ++k) v[k] = mont_mul(v[k], tw_tail_s[(u32)k * L + low]);
-        }
-        u64 *dst = S + col * P.cs + low + (low >> 4);
-#pragma unroll
-        for (int k = 0; k < M; ++k) dst[(u32)k * Lp] = v[k];
     }
-    if (TL == 0 || tid >= ngroups) tables_ready();  // every thread passes the wait exactly once
+    bool waited = false;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        const u32 g = tid + (u32)gi * nthreads;
+        if (g < ngroups) {
+            u32 col, low;
+            if (rowfast) {
+                low = g & (L - 1);
+                col = g >> log_L;
+            } else {
+                col = g & (T - 1);
+                low = g >> P.log_T;
+            }
+            if (P.in_scale) {
+#pragma unroll
+                for (int j = 0; j < M; ++j)
+                    v[gi][j] = mont_mul(v[gi][j], P.in_scale[(u32)bitrev4_c(j, TL) * L + low]);
+            }
+            if (TL > 0) {
+                dft4_dit<TL>(v[gi], P.w16, 16 >> TL);
+                v[gi][0] = canon4(v[gi][0]);
+                if (!waited) {
+                    tables_ready();
+                    waited = true;
+                }
+#pragma unroll
+                for (int k = 1; k < M; ++k) v[gi][k] = mont_mul(v[gi][k], tw_tail_s[(u32)k * L + low]);
+            }
+            u64 *dst = S + col * P.cs + low + (low >> 4);
+#pragma unroll
+            for (int k = 0; k < M; ++k) dst[(u32)k * Lp] = v[gi][k];
+        }
+    }
+    if (!waited) tables_ready();  // every thread passes the wait exactly once
 }
 
 // ---- core: one in-place 16-point step over the digit of weight L = 16^(a-1-s) -------------------

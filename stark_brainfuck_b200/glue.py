@@ -76,15 +76,35 @@ class Glue:
         return self.B.np_to_xfe(a, field) if kind == "x" else self.B.np_to_bfe(a[0], field)
 
     # ------------------------------------------------------------------ code/ntt.py
-    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None):
+    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None, lone_source=None):
         n = len(values) if n_out is None else n_out
         w = self.base_value(primitive_root, "primitive_root")
         # every 2-power root of unity of F_p^3 lies in F_p, so a root with higher
         # coefficients can never pass the order asserts of code/ntt.py:13-16
         assert w is not None, "primitive root must be nth root of unity, where n is %d" % n
-        d, kind, field = self._to_device(values)
-        out = self.engine.ntt(d, _ilog2(n), w, offset=offset, inverse=inverse)
-        return self._from_device(out, kind, field)
+        first = values[0]
+        if self.B.is_xfe(first):
+            arr, kind = self.B.xfe_to_np(values), "x"
+        elif self.B.is_bfe(first):
+            arr, kind = self.B.bfe_to_np(values).reshape(1, -1), "b"
+        else:
+            raise TypeError("cannot transform a list of %r" % type(first))
+        if kind == "x" and not inverse and arr[:, 0].any() and not arr[:, 1:].any():
+            return self._lone_coefficient_ntt(lone_source if lone_source is not None else first, w, n)
+        out = self.engine.ntt(self.engine.upload(arr), _ilog2(n), w, offset=offset, inverse=inverse)
+        return self._from_device(out, kind, first.field)
+
+    def _lone_coefficient_ntt(self, source, w, n):
+        """Forward transform of [x, 0, 0, ...] over the extension field.  The value is x everywhere;
+        what matters is identity: in the reference's recursion (code/ntt.py:23) every odd branch is
+        zero, `evens[i] + 0` returns the left polynomial (code/univariate.py:28-31) and the element
+        constructor re-wraps it (code/extension_field.py:6-9), so all n results are distinct elements
+        that SHARE x's coefficient objects -- visible in pickles (constant columns of
+        brainfuck_stark.prove(): SURVEY App. B5).  Same asserts as the device path."""
+        assert pow(w, n, P) == 1, "primitive root must be nth root of unity, where n is %d" % n
+        assert n < 2 or pow(w, n // 2, P) != 1, "primitive root is not primitive nth root of unity, where n is %d" % n
+        X = self.B.ExtensionFieldElement
+        return [X(source.polynomial, source.field) for _ in range(n)]
 
     def ntt(self, primitive_root, values):
         """code/ntt.py:4-23"""
@@ -120,7 +140,11 @@ class Glue:
         if off is None:  # genuinely extension-field offset: scale kernel, then plain ntt
             return self.ntt(generator, self.poly_scale(polynomial, offset).coefficients +
                             [offset.field.zero()] * (order - m))
-        return self._transform(generator, coeffs, False, offset=off, n_out=order)
+        lone = None
+        if self.B.is_xfe(coeffs[0]) and self.B.is_xfe(offset) and not coeffs[0].is_zero() \
+                and all(c.is_zero() for c in coeffs[1:]):
+            lone = (offset ^ 0) * coeffs[0]  # the scaled constant term, built by the caller's own classes
+        return self._transform(generator, coeffs, False, offset=off, n_out=order, lone_source=lone)
 
     def fast_coset_interpolate(self, offset, generator, values):
         """code/ntt.py:171-174: intt, then scale by offset^-1; all n coefficients are kept"""

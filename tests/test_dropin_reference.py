@@ -87,3 +87,52 @@ def test_uninstall_restores(reference_dropin):
     finally:
         from conftest import REFERENCE_DIR
         dropin.install(REFERENCE_DIR, engine=eng)
+
+
+def test_identity_graph_of_transform_outputs(reference_dropin):
+    """pickle memoises by identity: constant / zero / generic extension-field polynomials must give lists
+    whose pickles equal the reference's own (shared coefficient objects of constant columns)."""
+    import pickle
+    import random
+    from conftest import REFERENCE_DIR
+    from stark_brainfuck_b200 import dropin
+    import algebra
+    import extension_field
+    import fri as fri_mod
+    import ntt as ntt_mod
+    import univariate
+    xf = extension_field.ExtensionField.main()
+    bf = xf.modulus.coefficients[0].field
+    f = algebra.BaseField.main()
+    R = random.Random(99)
+
+    def X(*c):
+        return extension_field.ExtensionFieldElement(
+            univariate.Polynomial([algebra.BaseFieldElement(v, bf) for v in c]), xf)
+
+    n = 16
+    dom = fri_mod.Fri.Domain(f.generator(), f.primitive_nth_root(n), n)
+    P = 18446744069414584321
+    polys = {
+        "constant": univariate.Polynomial([X(5, 6, 7)]),
+        "constant_with_explicit_zeros": univariate.Polynomial([X(R.randrange(P), 1)] + [xf.zero()] * 3),
+        "zero": univariate.Polynomial([xf.zero()] * 2),
+        "generic": univariate.Polynomial([X(R.randrange(P), R.randrange(P), R.randrange(P)) for _ in range(4)]),
+        "leading_zero": univariate.Polynomial([xf.zero(), X(3)]),
+    }
+    lone = [X(9, 8, 7)] + [xf.zero()] * 7
+
+    def run():
+        out = {k: pickle.dumps(dom.xevaluate(p, xf)) for k, p in polys.items()}
+        out["ntt_lone"] = pickle.dumps(ntt_mod.ntt(xf.lift(f.primitive_nth_root(8)), lone))
+        return out
+
+    eng = reference_dropin.engine
+    got = run()
+    dropin.uninstall()
+    try:
+        want = run()
+    finally:
+        dropin.install(REFERENCE_DIR, engine=eng)
+    for k in want:
+        assert got[k] == want[k], k
