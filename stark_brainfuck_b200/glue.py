@@ -89,18 +89,47 @@ class Glue:
             arr, kind = self.B.bfe_to_np(values).reshape(1, -1), "b"
         else:
             raise TypeError("cannot transform a list of %r" % type(first))
-        if kind == "x" and not inverse and arr[:, 0].any() and not arr[:, 1:].any():
-            return self._lone_coefficient_ntt(lone_source if lone_source is not None else first, w, n)
+        share = 0
+        if kind == "x" and not inverse:
+            share = self._shared_output_period(arr, n)
+            if share == 1:
+                return self._lone_coefficient_ntt(lone_source if lone_source is not None else first, w, n)
         out = self.engine.ntt(self.engine.upload(arr), _ilog2(n), w, offset=offset, inverse=inverse)
+        if share:
+            # outputs i and i + share are the same sub-transform output with a zero odd partner all the
+            # way up: distinct elements wrapping the SAME coefficient objects (see _lone_coefficient_ntt)
+            base = self.B.np_to_xfe(self.engine.download(out)[:, :share], first.field)
+            X = self.B.ExtensionFieldElement
+            return [X(base[i % share].polynomial, first.field) for i in range(n)]
         return self._from_device(out, kind, first.field)
+
+    @staticmethod
+    def _shared_output_period(arr, n):
+        """Identity structure of the reference's recursive ntt on extension-field inputs
+        (code/ntt.py:20-23): `evens[i] + w^i * odds[i]` re-wraps the left operand's coefficient
+        objects whenever the odd branch is entirely zero (code/univariate.py:28-31,
+        code/extension_field.py:6-9).  With D = the fewest trailing zero bits among the indices
+        j >= 1 of non-zero inputs, the odd branches of the first D levels vanish, so outputs i and
+        i + n/2^D share their coefficient objects.  Returns that period n/2^D, 1 when only input 0
+        is non-zero (all outputs wrap ITS coefficient objects), 0 for the generic case (all fresh)
+        and for the zero vector.  (Accidental cancellations inside a non-zero branch are not
+        modelled: they need structured inputs of measure zero.)"""
+        nz = np.nonzero(arr.any(axis=0))[0]
+        if len(nz) == 0:
+            return 0
+        pos = nz[nz > 0]
+        if len(pos) == 0:
+            return 1
+        low = int(np.bitwise_or.reduce(pos))  # its lowest set bit = 2^D
+        period = n // (low & -low)
+        return 0 if period == n else period
 
     def _lone_coefficient_ntt(self, source, w, n):
         """Forward transform of [x, 0, 0, ...] over the extension field.  The value is x everywhere;
-        what matters is identity: in the reference's recursion (code/ntt.py:23) every odd branch is
-        zero, `evens[i] + 0` returns the left polynomial (code/univariate.py:28-31) and the element
-        constructor re-wraps it (code/extension_field.py:6-9), so all n results are distinct elements
-        that SHARE x's coefficient objects -- visible in pickles (constant columns of
-        brainfuck_stark.prove(): SURVEY App. B5).  Same asserts as the device path."""
+        what matters is identity: every odd branch of the reference's recursion is zero, so all n
+        results are distinct elements that SHARE x's coefficient objects -- visible in pickles
+        (constant columns of brainfuck_stark.prove(): SURVEY App. B5).  Same asserts as the device
+        path."""
         assert pow(w, n, P) == 1, "primitive root must be nth root of unity, where n is %d" % n
         assert n < 2 or pow(w, n // 2, P) != 1, "primitive root is not primitive nth root of unity, where n is %d" % n
         X = self.B.ExtensionFieldElement

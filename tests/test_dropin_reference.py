@@ -119,6 +119,9 @@ def test_identity_graph_of_transform_outputs(reference_dropin):
         "zero": univariate.Polynomial([xf.zero()] * 2),
         "generic": univariate.Polynomial([X(R.randrange(P), R.randrange(P), R.randrange(P)) for _ in range(4)]),
         "leading_zero": univariate.Polynomial([xf.zero(), X(3)]),
+        "c0_plus_c8_x8": univariate.Polynomial([X(4, 5)] + [xf.zero()] * 7 + [X(R.randrange(P), 2, 3)]),
+        "even_powers_only": univariate.Polynomial([X(1), xf.zero(), X(2, 2), xf.zero(), xf.zero(), xf.zero(), X(7)]),
+        "x4_only": univariate.Polynomial([xf.zero()] * 4 + [X(R.randrange(P))]),
     }
     lone = [X(9, 8, 7)] + [xf.zero()] * 7
 
