@@ -52,8 +52,62 @@ extern "C" int b2s_init(int device) {
     return 0;
 }
 
+// The host-buffer path keeps one pair of device staging buffers and one non-blocking stream
+// per thread (grown on demand, released by b2s_shutdown of that thread or at exit): a malloc/free
+// pair per call would cost more than the transform.
+namespace {
+struct HostPath {
+    cudaStream_t st = nullptr;
+    u64 *d_in = nullptr, *d_out = nullptr;
+    size_t cap_in = 0, cap_out = 0;
+    int dev = -1;
+};
+thread_local HostPath g_hp;
+
+int host_path_reserve(size_t n_in_elems, size_t n_out_elems) {
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    if (g_hp.dev != dev) {
+        if (g_hp.st) cudaStreamDestroy(g_hp.st);
+        if (g_hp.d_in) cudaFree(g_hp.d_in);
+        if (g_hp.d_out) cudaFree(g_hp.d_out);
+        g_hp = HostPath();
+        g_hp.dev = dev;
+        B2S_CUDA(cudaStreamCreateWithFlags(&g_hp.st, cudaStreamNonBlocking));
+    }
+    if (n_in_elems > g_hp.cap_in) {
+        if (g_hp.d_in) cudaFree(g_hp.d_in);
+        g_hp.d_in = nullptr;
+        B2S_CUDA(cudaMalloc(&g_hp.d_in, sizeof(u64) * n_in_elems));
+        g_hp.cap_in = n_in_elems;
+    }
+    if (n_out_elems > g_hp.cap_out) {
+        if (g_hp.d_out) cudaFree(g_hp.d_out);
+        g_hp.d_out = nullptr;
+        B2S_CUDA(cudaMalloc(&g_hp.d_out, sizeof(u64) * n_out_elems));
+        g_hp.cap_out = n_out_elems;
+    }
+    return 0;
+}
+
+int copy_planes(u64 *dst, u64 dst_stride, const u64 *src, u64 src_stride, u64 width, u32 n_planes, cudaMemcpyKind kind,
+                cudaStream_t st) {
+    if (n_planes == 1 || (dst_stride == width && src_stride == width)) {
+        B2S_CUDA(cudaMemcpyAsync(dst, src, sizeof(u64) * width * n_planes, kind, st));
+    } else {
+        B2S_CUDA(cudaMemcpy2DAsync(dst, sizeof(u64) * dst_stride, src, sizeof(u64) * src_stride, sizeof(u64) * width,
+                                   n_planes, kind, st));
+    }
+    return 0;
+}
+}  // namespace
+
 extern "C" int b2s_shutdown(void) {
     cudaDeviceSynchronize();
+    if (g_hp.st) cudaStreamDestroy(g_hp.st);
+    if (g_hp.d_in) cudaFree(g_hp.d_in);
+    if (g_hp.d_out) cudaFree(g_hp.d_out);
+    g_hp = HostPath();
     ntt_cache_clear();
     return 0;
 }
@@ -72,19 +126,15 @@ extern "C" int b2s_ntt_host(const uint64_t *h_in, uint64_t in_stride, uint32_t n
         return B2S_ERR_ARG;
     }
     const u64 n = (u64)1 << log_n;
-    cudaStream_t st = 0;
-    u64 *d_in = nullptr, *d_out = nullptr;
-    B2S_CUDA(cudaMallocAsync(&d_in, sizeof(u64) * (n_in ? n_in : 1) * n_planes, st));
-    B2S_CUDA(cudaMallocAsync(&d_out, sizeof(u64) * n * n_planes, st));
-    if (n_in)
-        B2S_CUDA(cudaMemcpy2DAsync(d_in, sizeof(u64) * n_in, h_in, sizeof(u64) * in_stride, sizeof(u64) * n_in, n_planes,
-                                   cudaMemcpyHostToDevice, st));
-    int rc = ntt_run(d_in, n_in, n_in, d_out, n, log_n, n_planes, omega, offset, inverse, st);
-    if (rc == 0)
-        B2S_CUDA(cudaMemcpy2DAsync(h_out, sizeof(u64) * out_stride, d_out, sizeof(u64) * n, sizeof(u64) * n, n_planes,
-                                   cudaMemcpyDeviceToHost, st));
-    cudaFreeAsync(d_in, st);
-    cudaFreeAsync(d_out, st);
+    int rc = host_path_reserve((size_t)(n_in ? n_in : 1) * n_planes, (size_t)n * n_planes);
+    if (rc) return rc;
+    cudaStream_t st = g_hp.st;
+    if (n_in) {
+        rc = copy_planes(g_hp.d_in, n_in, h_in, in_stride, n_in, n_planes, cudaMemcpyHostToDevice, st);
+        if (rc) return rc;
+    }
+    rc = ntt_run(g_hp.d_in, n_in, n_in, g_hp.d_out, n, log_n, n_planes, omega, offset, inverse, st);
+    if (rc == 0) rc = copy_planes(h_out, out_stride, g_hp.d_out, n, n, n_planes, cudaMemcpyDeviceToHost, st);
     B2S_CUDA(cudaStreamSynchronize(st));
     return rc;
 }
