@@ -287,6 +287,12 @@ def run_b200(args):
     e2e_val = world * muls / (e2e_ms / 1e3)
     peak, which = peaks()
     achieved = 16.0 * n / (fwd / 1e3) / 1e9
+    traffic = None
+    try:  # DRAM bytes of the two pass launches from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "ntt_traffic.json")) as f:
+            traffic = int(json.load(f)["dram_bytes_per_transform"])
+    except Exception:
+        pass
 
     # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) ------
     from oracle import oracle as orc
@@ -311,7 +317,7 @@ def run_b200(args):
                 "path": "b2s_ntt_host (C ABI, pinned host buffers) forward then inverse"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": which,
+                     "traffic": traffic, "peak_source": which,
                      "kernel": "ntt4_pass_kernel x2 (forward 2^20 transform, input not L2-resident)",
                      "algorithmic_bytes": 16 * n, "duration_ms": fwd},
         "cpu_baseline": {"value": muls / cpu_dt, "unit": UNIT, "cores": 1, "kind": "port",
