@@ -144,6 +144,34 @@ int b2s_fri_fold(const uint64_t *d_cw, uint64_t cw_stride, uint64_t N, const uin
 int b2s_gather(const uint64_t *d_planes, uint64_t plane_stride, uint32_t n_planes, const uint64_t *h_indices,
                uint32_t n_indices, uint64_t *h_out, void *stream);
 
+/* ---- quotient codewords ---------------------------------------
+ * code/table.py:155-178 boundary_quotients, :190-236 transition_quotients, :253-286
+ * terminal_quotients and code/permutation_argument.py:11-20 quotient: for every point
+ * x_i = offset * omega^i of the FRI domain (code/fri.py:20-21) and every constraint c
+ *     out[c][i] = ( sum_m coeff[m] * prod_f var(v_f)[i] ^ e_f ) * zinv(x_i)
+ * which is code/multivariate.py:105-116 MPolynomial.evaluate at the point
+ *     var(v)[i] = cw[v][i]                        for v <  width
+ *               = cw[v - width][(i + shift) % N]  for v >= width   (the "next row" variables)
+ * times the inverse zerofier:
+ *     B2S_ZEROFIER_BOUNDARY    (x_i - 1)^-1                               code/table.py:161-163
+ *     B2S_ZEROFIER_TRANSITION  (x_i^height - 1)^-1 * (x_i - omicron_inv)  code/table.py:194-201
+ *                              (height == 0: zero, as in the reference)
+ *     B2S_ZEROFIER_TERMINAL    (x_i - omicron_inv)^-1                     code/table.py:256-259
+ * d_cw: `width` extension-field codewords, codeword v = planes d_cw + (3 v + s) * N, s < 3.
+ * The constraint program is given in HOST memory: constraint c owns the monomials
+ * h_mono_off[c] .. h_mono_off[c+1]; monomial m has coefficient h_coeffs[3 m .. 3 m + 2] and
+ * factors h_factors[m * max_factors + f] = (variable << 8) | exponent, exponent 0 = unused.
+ * d_out: n_constraints codewords in the same plane layout.  *h_zero_flag is set to 1 when a
+ * zerofier vanishes on the domain (the reference's batch_inverse asserts, code/ntt.py:178-179).
+ * Synchronises. */
+#define B2S_ZEROFIER_BOUNDARY 1
+#define B2S_ZEROFIER_TRANSITION 2
+#define B2S_ZEROFIER_TERMINAL 3
+int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, uint64_t shift, uint32_t n_constraints,
+                  const uint32_t *h_mono_off, const uint64_t *h_coeffs, const uint32_t *h_factors, uint32_t max_factors,
+                  uint32_t zerofier_kind, uint64_t height, uint64_t omicron_inv, uint64_t offset, uint64_t omega,
+                  uint64_t *d_out, int *h_zero_flag, void *stream);
+
 /* ---- multi-GPU exchange step of the four-step NTT (no counterpart in the single-process
  * reference) ------------------------------------------------------------
  * n = n1*n2, j = j1 + n1*j2.  The caller owns `rows` = n1/G columns j1 (first one: row_base) as

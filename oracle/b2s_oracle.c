@@ -288,6 +288,84 @@ void orc_fri_fold(const u64 *cw, u64 stride, u64 N, const u64 alpha[3], u64 offs
     }
 }
 
+/* ---------------------------------------------------------------- quotient codewords */
+/* code/multivariate.py:105-116 MPolynomial.evaluate: acc = sum over monomials of
+ * coefficient * prod_i point[i]^k[i], in the order of the flattened dictionary. */
+static void xpow_small(const u64 a[3], u32 e, u64 r[3]) {
+    u64 acc[3] = {1, 0, 0}, t[3];
+    for (u32 k = 0; k < e; ++k) {
+        orc_xmul(acc, a, t);
+        memcpy(acc, t, sizeof(t));
+    }
+    memcpy(r, acc, sizeof(acc));
+}
+
+/* code/table.py:155-178, :190-236, :253-286 and code/permutation_argument.py:11-20 for one table:
+ * out[c][i] = mpo_c.evaluate(point_i) * lift(zerofier_inverse[i]) over the domain offset*omega^i.
+ * cw: `width` extension-field codewords of N values (planes c0,c1,c2 of codeword v at 3v, 3v+1, 3v+2);
+ * variables >= width read row (i + shift) mod N.  zerofier kinds: 1 boundary (x - 1)^-1,
+ * 2 transition (x^height - 1)^-1 (x - omicron_inv) or 0 when height == 0, 3 terminal (x - omicron_inv)^-1.
+ * Returns 1 if a zerofier vanishes on the domain (the reference's batch_inverse asserts), else 0. */
+int orc_quotients(const u64 *cw, u64 N, u32 width, u64 shift, u32 n_constraints, const u32 *mono_off,
+                  const u64 *coeffs, const u32 *factors, u32 max_factors, u32 kind, u64 height, u64 omicron_inv,
+                  u64 offset, u64 omega, u64 *out) {
+    int flag = 0;
+    u64 wi = 1;
+    for (u64 i = 0; i < N; ++i) {
+        const u64 x = orc_mul(offset, wi);
+        u64 zinv;
+        if (kind == 1) {
+            const u64 z = orc_sub(x, 1);
+            flag |= z == 0;
+            zinv = orc_inv(z);
+        } else if (kind == 2) {
+            if (height == 0) {
+                zinv = 0;
+            } else {
+                const u64 z = orc_sub(orc_pow(x, height), 1);
+                flag |= z == 0;
+                zinv = orc_mul(orc_inv(z), orc_sub(x, omicron_inv));
+            }
+        } else {
+            const u64 z = orc_sub(x, omicron_inv);
+            flag |= z == 0;
+            zinv = orc_inv(z);
+        }
+        const u64 inext = (i + shift) % N;
+        for (u32 c = 0; c < n_constraints; ++c) {
+            u64 acc[3] = {0, 0, 0};
+            for (u32 m = mono_off[c]; m < mono_off[c + 1]; ++m) {
+                u64 prod[3] = {coeffs[3 * m], coeffs[3 * m + 1], coeffs[3 * m + 2]}, t[3], pw[3];
+                for (u32 f = 0; f < max_factors; ++f) {
+                    const u32 fac = factors[m * max_factors + f], e = fac & 0xFF;
+                    if (!e) continue;
+                    u32 v = fac >> 8;
+                    u64 at = i;
+                    if (v >= width) {
+                        v -= width;
+                        at = inext;
+                    }
+                    const u64 xv[3] = {cw[(3 * (u64)v) * N + at], cw[(3 * (u64)v + 1) * N + at],
+                                       cw[(3 * (u64)v + 2) * N + at]};
+                    xpow_small(xv, e, pw);
+                    orc_xmul(prod, pw, t);
+                    memcpy(prod, t, sizeof(t));
+                }
+                orc_xadd(acc, prod, t);
+                memcpy(acc, t, sizeof(t));
+            }
+            const u64 zl[3] = {zinv, 0, 0};
+            u64 q[3];
+            orc_xmul(acc, zl, q);
+            out[(3 * (u64)c) * N + i] = q[0];
+            out[(3 * (u64)c + 1) * N + i] = q[1];
+            out[(3 * (u64)c + 2) * N + i] = q[2];
+        }
+        wi = orc_mul(wi, omega);
+    }
+    return flag;
+}
+
 /* ---------------------------------------------------------------- BLAKE2b-512 (RFC 7693) */
 static const u64 B2B_IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL,
                               0xa54ff53a5f1d36f1ULL, 0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL,

@@ -71,6 +71,9 @@ def lib():
         L.orc_xeval_points.argtypes = [vp, u64, u64, vp, u64, vp, u64, u64]
         L.orc_fri_fold.restype = None
         L.orc_fri_fold.argtypes = [vp, u64, u64, vp, u64, u64, vp, u64]
+        L.orc_quotients.argtypes = [vp, u64, C.c_uint32, u64, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, u64, u64,
+                                    u64, u64, vp]
+        L.orc_quotients.restype = C.c_int
         L.orc_blake2b.restype = None
         L.orc_blake2b.argtypes = [C.c_char_p, u64, vp]
         L.orc_pickle_uint.restype = C.c_uint32
@@ -214,6 +217,23 @@ def fri_fold(cw, alpha, offset, omega):
     out = np.empty((3, n // 2), dtype=np.uint64)
     lib().orc_fri_fold(_p(cw), n, n, _x3(alpha), offset, omega, _p(out), n // 2)
     return out
+
+
+def quotients(cw, shift, mono_off, coeffs, factors, kind, height, omicron_inv, offset, omega):
+    """code/table.py:155-286 / code/permutation_argument.py:11-20 for one table.
+    cw: (width, 3, N) uint64; mono_off (C+1,) uint32; coeffs (M, 3) uint64; factors (M, F) uint32
+    ((variable << 8) | exponent).  Returns ((C, 3, N) uint64, zerofier_vanishes flag)."""
+    cw = np.ascontiguousarray(cw, dtype=np.uint64)
+    width, _, n = cw.shape
+    mono_off = np.ascontiguousarray(mono_off, dtype=np.uint32)
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
+    factors = np.ascontiguousarray(factors, dtype=np.uint32).reshape(len(coeffs), -1)
+    nc = len(mono_off) - 1
+    out = np.zeros((nc, 3, n), dtype=np.uint64)
+    flag = lib().orc_quotients(_p(cw), n, width, shift, nc, mono_off.ctypes.data_as(C.c_void_p),
+                               coeffs.ctypes.data_as(C.c_void_p), factors.ctypes.data_as(C.c_void_p),
+                               factors.shape[1] if factors.size else 0, kind, height, omicron_inv, offset, omega, _p(out))
+    return out, bool(flag)
 
 
 # ---- hashing / pickle / Merkle ---------------------------------------------

@@ -1,0 +1,156 @@
+// quotient.cu -- quotient codewords of the AIR constraints.
+//
+// Replaces the per-point Python loops of code/table.py:155-286 and
+// code/permutation_argument.py:11-20: every constraint is a multivariate polynomial
+// (code/multivariate.py: dict exponent-vector -> coefficient) that the reference evaluates at
+// every point of the FRI domain with MPolynomial.evaluate (code/multivariate.py:105-116) and
+// divides by a zerofier.  Here the host flattens the dictionaries into a monomial program and
+// one thread evaluates one (constraint, point) pair in extension-field arithmetic; the inverse
+// zerofier is computed once per point by a first kernel.  HBM-bound only in name: a point reads
+// 24 B per variable it uses and writes 24 B, the monomial arithmetic dominates.
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ xfe x_pow_small(xfe a, u32 e) {
+    xfe acc = {{1, 0, 0}};
+    while (e) {
+        if (e & 1) acc = x_mul(acc, a);
+        e >>= 1;
+        if (e) a = x_mul(a, a);
+    }
+    return acc;
+}
+
+struct ZeroParams {
+    u64 w_sq[32];  // omega^(2^b)
+    u64 offset, omicron_inv, height;
+    u32 kind;
+};
+
+// zinv[i] = inverse zerofier at x_i = offset * omega^i; *flag = 1 if a zerofier vanishes
+__global__ void __launch_bounds__(256) zerofier_kernel(const __grid_constant__ ZeroParams Z, u64 N, u64 *zinv, int *flag) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const u64 x = gl_mul(Z.offset, gl_pow_sq(Z.w_sq, i));
+    u64 r;
+    if (Z.kind == B2S_ZEROFIER_BOUNDARY) {
+        const u64 z = gl_sub(x, 1);
+        if (z == 0) *flag = 1;
+        r = gl_inv(z);
+    } else if (Z.kind == B2S_ZEROFIER_TRANSITION) {
+        if (Z.height == 0) {
+            r = 0;  // x^0 - 1 = 0 is used as is (code/table.py:196-199)
+        } else {
+            const u64 z = gl_sub(gl_pow(x, Z.height), 1);
+            if (z == 0) *flag = 1;
+            r = gl_mul(gl_inv(z), gl_sub(x, Z.omicron_inv));
+        }
+    } else {
+        const u64 z = gl_sub(x, Z.omicron_inv);
+        if (z == 0) *flag = 1;
+        r = gl_inv(z);
+    }
+    zinv[i] = r;
+}
+
+__global__ void __launch_bounds__(128)
+    quotient_kernel(const u64 *__restrict__ cw, u64 N, u32 width, u64 shift, const u32 *__restrict__ mono_off,
+                    const u64 *__restrict__ coeffs, const u32 *__restrict__ factors, u32 max_factors,
+                    const u64 *__restrict__ zinv, u64 *__restrict__ out) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 c = blockIdx.y;
+    if (i >= N) return;
+    u64 inext = i + shift;
+    if (inext >= N) inext -= N;
+    xfe acc = {{0, 0, 0}};
+    for (u32 m = mono_off[c]; m < mono_off[c + 1]; ++m) {
+        xfe prod = {{coeffs[3 * m], coeffs[3 * m + 1], coeffs[3 * m + 2]}};
+        for (u32 f = 0; f < max_factors; ++f) {
+            const u32 fac = factors[m * max_factors + f];
+            const u32 e = fac & 0xFF;
+            if (e == 0) continue;
+            u32 v = fac >> 8;
+            u64 at = i;
+            if (v >= width) {
+                v -= width;
+                at = inext;
+            }
+            const u64 *p = cw + (u64)3 * v * N + at;
+            const xfe x = {{p[0], p[N], p[2 * N]}};
+            prod = x_mul(prod, x_pow_small(x, e));
+        }
+        acc = x_add(acc, prod);
+    }
+    const xfe q = x_mul_base(acc, zinv[i]);
+    u64 *o = out + (u64)3 * c * N + i;
+    o[0] = q.c[0];
+    o[N] = q.c[1];
+    o[2 * N] = q.c[2];
+}
+
+}  // namespace
+
+extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, uint64_t shift, uint32_t n_constraints,
+                             const uint32_t *h_mono_off, const uint64_t *h_coeffs, const uint32_t *h_factors,
+                             uint32_t max_factors, uint32_t zerofier_kind, uint64_t height, uint64_t omicron_inv,
+                             uint64_t offset, uint64_t omega, uint64_t *d_out, int *h_zero_flag, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0 || (N & (N - 1)) || shift >= N || width == 0 || zerofier_kind < 1 || zerofier_kind > 3) {
+        b2s_set_error("quotients: bad arguments (N %llu, width %u, shift %llu, zerofier %u)", (unsigned long long)N, width,
+                      (unsigned long long)shift, zerofier_kind);
+        return B2S_ERR_ARG;
+    }
+    if (h_zero_flag) *h_zero_flag = 0;
+    if (n_constraints == 0) return 0;
+    const u32 n_mono = h_mono_off[n_constraints];
+    const u32 mf = max_factors ? max_factors : 1;
+    for (u32 m = 0; m < n_mono; ++m)
+        for (u32 f = 0; f < max_factors; ++f) {
+            const u32 fac = h_factors[m * max_factors + f];
+            if ((fac & 0xFF) && (fac >> 8) >= 2 * width) {
+                b2s_set_error("quotients: monomial %u uses variable %u of %u", m, fac >> 8, 2 * width);
+                return B2S_ERR_ARG;
+            }
+        }
+    // the program: a few KB, uploaded per call
+    u32 *d_off = nullptr, *d_fac = nullptr;
+    u64 *d_coef = nullptr, *d_zinv = nullptr;
+    int *d_flag = nullptr;
+    B2S_CUDA(cudaMallocAsync(&d_off, sizeof(u32) * (n_constraints + 1), st));
+    B2S_CUDA(cudaMallocAsync(&d_fac, sizeof(u32) * ((size_t)n_mono * mf + 1), st));
+    B2S_CUDA(cudaMallocAsync(&d_coef, sizeof(u64) * (3 * (size_t)n_mono + 1), st));
+    B2S_CUDA(cudaMallocAsync(&d_zinv, sizeof(u64) * N, st));
+    B2S_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
+    B2S_CUDA(cudaMemcpyAsync(d_off, h_mono_off, sizeof(u32) * (n_constraints + 1), cudaMemcpyHostToDevice, st));
+    if (n_mono) {
+        B2S_CUDA(cudaMemcpyAsync(d_fac, h_factors, sizeof(u32) * (size_t)n_mono * max_factors, cudaMemcpyHostToDevice, st));
+        B2S_CUDA(cudaMemcpyAsync(d_coef, h_coeffs, sizeof(u64) * 3 * (size_t)n_mono, cudaMemcpyHostToDevice, st));
+    }
+    B2S_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    ZeroParams Z;
+    u64 sq = omega;
+    for (int b = 0; b < 32; ++b) {
+        Z.w_sq[b] = sq;
+        sq = gl_mul(sq, sq);
+    }
+    Z.offset = offset;
+    Z.omicron_inv = omicron_inv;
+    Z.height = height;
+    Z.kind = zerofier_kind;
+    zerofier_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(Z, N, d_zinv, d_flag);
+    B2S_LAUNCHED();
+    quotient_kernel<<<dim3((unsigned)((N + 127) / 128), n_constraints), 128, 0, st>>>(d_cw, N, width, shift, d_off, d_coef,
+                                                                                      d_fac, max_factors, d_zinv, d_out);
+    B2S_LAUNCHED();
+    int flag = 0;
+    B2S_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    cudaFreeAsync(d_off, st);
+    cudaFreeAsync(d_fac, st);
+    cudaFreeAsync(d_coef, st);
+    cudaFreeAsync(d_zinv, st);
+    cudaFreeAsync(d_flag, st);
+    B2S_CUDA(cudaStreamSynchronize(st));
+    if (h_zero_flag) *h_zero_flag = flag;
+    return 0;
+}

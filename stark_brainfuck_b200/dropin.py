@@ -14,6 +14,7 @@ time lives in every importing module's globals.  install() therefore
 uninstall() restores every original (needed to time the CPU reference in the same process).
 """
 import importlib
+import os
 import sys
 
 from .glue import Glue
@@ -32,9 +33,10 @@ def current_glue():
     return _state["glue"] if _state else None
 
 
-def install(reference_dir=None, engine=None):
+def install(reference_dir=None, engine=None, quotients=True):
     """Patch the reference modules importable from `reference_dir` (or already on sys.path).
-    Returns the Glue in use."""
+    `quotients=True` also moves the quotient-codeword loops of table.py / permutation_argument.py
+    (93 % of prove()) to the device.  Returns the Glue in use."""
     global _state
     if _state is not None:
         return _state["glue"]
@@ -81,6 +83,28 @@ def install(reference_dir=None, engine=None):
     set_attr(Fri, "prove", lambda self, codeword, proof_stream: glue.fri_prove(self, codeword, proof_stream))
     set_attr(Merkle, "__init__", lambda self, data_array: glue.merkle_build(self, data_array))
     set_attr(Merkle, "open", lambda self, index: glue.merkle_open(self, index))
+
+    # -- 4. next row: quotient codewords of the AIR ---------------------------
+    # DEBUG keeps the reference's own loops (they print and assert degree bounds on the way).
+    if quotients:
+        table = importlib.import_module("table")
+        pa = importlib.import_module("permutation_argument")
+        mv = importlib.import_module("multivariate")
+        T = table.Table
+        orig_b, orig_t, orig_e = T.boundary_quotients, T.transition_quotients, T.terminal_quotients
+        orig_q = pa.PermutationArgument.quotient
+        debug = lambda: os.environ.get("DEBUG") is not None  # noqa: E731
+        set_attr(T, "boundary_quotients", lambda self, fri_domain, codewords, challenges:
+                 orig_b(self, fri_domain, codewords, challenges) if debug()
+                 else glue.table_boundary_quotients(self, fri_domain, codewords, challenges))
+        set_attr(T, "transition_quotients", lambda self, domain, codewords, challenges:
+                 orig_t(self, domain, codewords, challenges) if debug()
+                 else glue.table_transition_quotients(self, domain, codewords, challenges))
+        set_attr(T, "terminal_quotients", lambda self, domain, codewords, challenges, terminals:
+                 orig_e(self, domain, codewords, challenges, terminals) if debug()
+                 else glue.table_terminal_quotients(self, domain, codewords, challenges, terminals))
+        set_attr(pa.PermutationArgument, "quotient", lambda self, fri_domain:
+                 orig_q(self, fri_domain) if debug() else glue.permutation_quotient(self, fri_domain, mv.MPolynomial))
 
     _state = {"glue": glue, "saved": saved, "mods": mods}
     return glue

@@ -175,6 +175,25 @@ class Engine:
                                          _ptr(nodes) if nodes is not None else None, self.stream_ptr()))
         return nxt, nodes
 
+    # ---- quotient codewords ---------------------------------
+    def quotients(self, cw, shift, mono_off, coeffs, factors, kind, height, omicron_inv, offset, omega):
+        """code/table.py:155-286 for one table.  cw: (width, 3, N) int64 device tensor; the constraint
+        program as numpy arrays (mono_off (C+1,) uint32, coeffs (M, 3) uint64, factors (M, F) uint32).
+        Returns ((C, 3, N) device tensor, True if a zerofier vanishes on the domain)."""
+        width, three, N = cw.shape
+        assert three == 3 and cw.is_contiguous()
+        mono_off = np.ascontiguousarray(mono_off, dtype=np.uint32)
+        nc = len(mono_off) - 1
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
+        factors = np.ascontiguousarray(factors, dtype=np.uint32).reshape(len(coeffs), -1)
+        out = torch.empty((nc, 3, N), dtype=torch.int64, device=self.device)
+        flag = C.c_int(0)
+        self.check(self.lib.b2s_quotients(_ptr(cw), N, width, shift, nc, mono_off.ctypes.data_as(C.c_void_p),
+                                          coeffs.ctypes.data_as(C.c_void_p), factors.ctypes.data_as(C.c_void_p),
+                                          factors.shape[1] if factors.size else 0, kind, height, omicron_inv, offset,
+                                          omega, _ptr(out), C.byref(flag), self.stream_ptr()))
+        return out, bool(flag.value)
+
     def gather(self, planes, indices):
         """planes[:, indices] to the host as numpy (len(indices), q) uint64"""
         q, n = planes.shape

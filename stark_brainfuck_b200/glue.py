@@ -268,6 +268,74 @@ class Glue:
         xfield = values[0].field
         return self.fast_coset_interpolate(xfield.lift(dom.offset), xfield.lift(dom.omega), values)
 
+    # ------------------------------------------------------------------ code/table.py quotients
+    def compile_constraints(self, constraints, n_vars):
+        """Flatten MPolynomials (code/multivariate.py: dict exponent-vector -> coefficient) into the
+        monomial program of b2s_quotients.  Same checks as MPolynomial.evaluate (:105-116)."""
+        mono_off, coeffs, facs = [0], [], []
+        for mpo in constraints:
+            for k, v in mpo.dictionary.items():
+                assert n_vars == len(k), \
+                    f"number of elements in point {n_vars} does not match with number of variables {len(k)} for polynomial {str(mpo)}"
+                if self.B.is_xfe(v):
+                    c = [co.value for co in v.polynomial.coefficients]
+                else:
+                    c = [v.value]
+                coeffs.append(c + [0] * (3 - len(c)))
+                f = [(i << 8) | e for i, e in enumerate(k) if e]
+                if any(e > 255 for e in k):
+                    raise ValueError("exponent above 255 in a constraint polynomial")
+                facs.append(f)
+            mono_off.append(len(coeffs))
+        width = max([len(f) for f in facs] + [1])
+        factors = np.zeros((len(facs), width), dtype=np.uint32)
+        for m, f in enumerate(facs):
+            factors[m, :len(f)] = f
+        return (np.asarray(mono_off, dtype=np.uint32), np.asarray(coeffs, dtype=np.uint64).reshape(-1, 3), factors)
+
+    def quotient_codewords(self, domain, codewords, width, constraints, kind, height=0, omicron_inv=1, shift=0):
+        """code/table.py:155-178 / :190-236 / :253-286: [mpo.evaluate(point_i) * lift(zerofier_inverse[i])]
+        for every constraint over the whole FRI domain, on the device."""
+        N = domain.length
+        n_vars = 2 * width if kind == ZEROFIER_TRANSITION else width
+        program = self.compile_constraints(constraints, n_vars)
+        xfield = codewords[0][0].field  # acc = point[0].field.zero() (code/multivariate.py:106)
+        planes = np.stack([self.B.xfe_to_np(codewords[j]) for j in range(width)])
+        cw = self.engine.upload(planes.reshape(3 * width, N)).reshape(width, 3, N)
+        out, vanishes = self.engine.quotients(cw, shift, *program, kind, height, omicron_inv, domain.offset.value,
+                                              domain.omega.value)
+        # code/ntt.py:178-179
+        assert not vanishes, "batch inverse does not work when input contains a zero"
+        a = self.engine.download(out.reshape(-1, N)).reshape(-1, 3, N)
+        return [self.B.np_to_xfe(a[c], xfield) for c in range(a.shape[0])]
+
+    def table_boundary_quotients(self, table, fri_domain, codewords, challenges):
+        """code/table.py:155-178"""
+        assert len(codewords) != 0, "'codewords' argument must have nonzero length"
+        return self.quotient_codewords(fri_domain, codewords, table.full_width, table.boundary_constraints_ext(challenges),
+                                       ZEROFIER_BOUNDARY)
+
+    def table_transition_quotients(self, table, domain, codewords, challenges):
+        """code/table.py:190-236"""
+        return self.quotient_codewords(domain, codewords, table.full_width, table.transition_constraints_ext(challenges),
+                                       ZEROFIER_TRANSITION, height=table.height,
+                                       omicron_inv=table.omicron.inverse().value,
+                                       shift=table.unit_distance(domain.length))
+
+    def table_terminal_quotients(self, table, domain, codewords, challenges, terminals):
+        """code/table.py:253-286"""
+        return self.quotient_codewords(domain, codewords, table.full_width,
+                                       table.terminal_constraints_ext(challenges, terminals), ZEROFIER_TERMINAL,
+                                       omicron_inv=table.omicron.inverse().value)
+
+    def permutation_quotient(self, pa, fri_domain, MPolynomial):
+        """code/permutation_argument.py:11-20: (lhs - rhs) * lift(1 / (x - 1)) as a two-variable program"""
+        lhs = pa.all_tables[pa.lhs[0]].codewords[pa.lhs[1]]
+        rhs = pa.all_tables[pa.rhs[0]].codewords[pa.rhs[1]]
+        xfield = lhs[0].field
+        difference = MPolynomial({(1, 0): xfield.one(), (0, 1): -xfield.one()})
+        return self.quotient_codewords(fri_domain, [lhs, rhs], 2, [difference], ZEROFIER_BOUNDARY)[0]
+
     # ------------------------------------------------------------------ code/merkle.py
     def merkle_build(self, tree, data_array, device_planes=None, device_nodes=None, leaf_cache=None,
                      canonical=None):
@@ -422,6 +490,9 @@ def prefetch_paths(tree, indices):
     nodes = getattr(tree, "nodes", None)
     if isinstance(nodes, NodeView):
         nodes.prefetch_paths(indices, tree.depth)
+
+
+ZEROFIER_BOUNDARY, ZEROFIER_TRANSITION, ZEROFIER_TERMINAL = 1, 2, 3
 
 
 class DeviceCodeword:

@@ -145,6 +145,21 @@ class FakeLib:
         return 0
 
 
+    def b2s_quotients(self, d_cw, N, width, shift, nc, h_off, h_coeffs, h_factors, max_factors, kind, height, oinv,
+                      offset, omega, d_out, h_flag, stream):
+        self.launches += 1
+        cw = _u64(_addr(d_cw), width * 3 * N).reshape(width, 3, N)
+        off = np.ctypeslib.as_array((C.c_uint32 * (nc + 1)).from_address(_addr(h_off)))
+        m = int(off[nc])
+        coeffs = _u64(_addr(h_coeffs), 3 * m).reshape(m, 3) if m else np.zeros((0, 3), dtype=np.uint64)
+        fac = (np.ctypeslib.as_array((C.c_uint32 * (m * max_factors)).from_address(_addr(h_factors)))
+               .reshape(m, max_factors) if m * max_factors else np.zeros((m, 0), dtype=np.uint32))
+        out, flag = orc.quotients(cw, shift, off, coeffs, fac, kind, height, oinv, offset, omega)
+        if nc:
+            _u64(_addr(d_out), nc * 3 * N).reshape(nc, 3, N)[:] = out
+        h_flag._obj.value = int(flag)
+        return 0
+
     def b2s_dist_twiddle_transpose(self, d_in, in_stride, rows, cols, row_base, omega, tw_mul, out_ptrs, n_peers,
                                    out_row_stride, out_col_offset, stream):
         self.launches += 1

@@ -11,7 +11,7 @@ little-endian u64 values; ExtensionFieldElement = c0,c1,c2 with trimmed
 coefficients zero-filled, elements in list order.
 
 Usage:  python tests/golden/make_golden.py <group> [...]
-Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs
+Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients
 Heavy groups are meant to run in the background, one process each.
 """
 import hashlib
@@ -479,6 +479,70 @@ def group_bfs():
                       "fri_domain_length": bfs.fri.domain.length, "prove_seconds": round(dt, 1)})
 
 
+def group_quotients():
+    """Table.boundary/transition/terminal_quotients (code/table.py:155-286) and
+    PermutationArgument.quotient (code/permutation_argument.py:11-20) of the unmodified reference on toy
+    tables with seeded random constraint polynomials; inputs are stored in full (they are small), the
+    constraint dictionaries as (exponent vector, coefficient) lists in dictionary order."""
+    from multivariate import MPolynomial
+    from permutation_argument import PermutationArgument
+    from table import Table
+    R = random.Random(31337)
+    N, W = 64, 3
+    dom = Fri.Domain(field.generator(), field.primitive_nth_root(N), N)
+
+    def rx():
+        return X(R.randrange(P), R.randrange(P), R.randrange(P))
+
+    def mpoly(n_vars, n_mono):
+        d = {}
+        for _ in range(n_mono):
+            k = [0] * n_vars
+            for _ in range(R.randrange(0, 4)):
+                k[R.randrange(n_vars)] += R.randrange(1, 4)
+            d[tuple(k)] = rx() if R.random() < 0.8 else X(R.randrange(5))
+        return MPolynomial(d)
+
+    class Toy(Table):
+        def __init__(self, length):
+            super().__init__(xfield, 2, W, length, 1, field.primitive_nth_root(N), N)
+            self.b = [mpoly(W, 3), mpoly(W, 1), MPolynomial(dict())]
+            self.t = [mpoly(2 * W, 6), mpoly(2 * W, 2)]
+            self.e = [mpoly(W, 4)]
+
+        def boundary_constraints_ext(self, challenges):
+            return self.b
+
+        def transition_constraints_ext(self, challenges):
+            return self.t
+
+        def terminal_constraints_ext(self, challenges, terminals):
+            return self.e
+
+    def program(constraints):
+        return [[[list(k), xfe_triple(v)] for k, v in c.dictionary.items()] for c in constraints]
+
+    out = {"N": N, "width": W, "offset": dom.offset.value, "omega": dom.omega.value, "tables": []}
+    tables = [Toy(5), Toy(0), Toy(16)]
+    for t in tables:
+        t.codewords = [[rx() for _ in range(N)] for _ in range(W)]
+        t.codewords[1][3] = xfield.zero()
+        t.codewords[2][7] = X(11)
+        res = {"height": t.height, "omicron_inv": t.omicron.inverse().value, "unit_distance": t.unit_distance(N),
+               "codewords": [[xfe_triple(x) for x in cw] for cw in t.codewords],
+               "boundary": {"program": program(t.b),
+                            "out": [[xfe_triple(x) for x in q] for q in t.boundary_quotients(dom, t.codewords, None)]},
+               "transition": {"program": program(t.t),
+                              "out": [[xfe_triple(x) for x in q] for q in t.transition_quotients(dom, t.codewords, None)]},
+               "terminal": {"program": program(t.e),
+                            "out": [[xfe_triple(x) for x in q]
+                                    for q in t.terminal_quotients(dom, t.codewords, None, None)]}}
+        out["tables"].append(res)
+    pa = PermutationArgument(tables, (0, 1), (2, 2))
+    out["permutation"] = {"lhs": [0, 1], "rhs": [2, 2], "out": [xfe_triple(x) for x in pa.quotient(dom)]}
+    dump("quotients.json", out)
+
+
 if __name__ == "__main__":
     for grp in sys.argv[1:]:
         if grp == "small":
@@ -493,5 +557,7 @@ if __name__ == "__main__":
             group_xntt_big()
         elif grp == "bfs":
             group_bfs()
+        elif grp == "quotients":
+            group_quotients()
         else:
             raise SystemExit("unknown group " + grp)

@@ -139,3 +139,92 @@ def test_identity_graph_of_transform_outputs(reference_dropin):
         dropin.install(REFERENCE_DIR, engine=eng)
     for k in want:
         assert got[k] == want[k], k
+
+
+def test_quotient_codewords_match_reference(reference_dropin):
+    """Table.boundary/transition/terminal_quotients and PermutationArgument.quotient on
+    the device path against the reference's own per-point loops (values and pickles), on a toy table."""
+    import pickle
+    import random
+    from conftest import REFERENCE_DIR
+    from stark_brainfuck_b200 import dropin
+    import algebra
+    import extension_field
+    import fri as fri_mod
+    import multivariate
+    import permutation_argument
+    import table
+    import univariate
+    P = 18446744069414584321
+    R = random.Random(4242)
+    f = algebra.BaseField.main()
+    xf = extension_field.ExtensionField.main()
+    bf = xf.modulus.coefficients[0].field
+
+    def X(*c):
+        return extension_field.ExtensionFieldElement(
+            univariate.Polynomial([algebra.BaseFieldElement(v, bf) for v in c]), xf)
+
+    def rx():
+        return X(R.randrange(P), R.randrange(P), R.randrange(P))
+
+    N, W = 64, 3
+    dom = fri_mod.Fri.Domain(f.generator(), f.primitive_nth_root(N), N)
+
+    def mpoly(n_vars, n_mono):
+        d = {}
+        for _ in range(n_mono):
+            k = [0] * n_vars
+            for _ in range(R.randrange(0, 4)):
+                k[R.randrange(n_vars)] += R.randrange(1, 4)
+            d[tuple(k)] = rx() if R.random() < 0.8 else X(R.randrange(5))
+        return multivariate.MPolynomial(d)
+
+    class Toy(table.Table):
+        def __init__(self, length):
+            super().__init__(xf, 2, W, length, 1, f.primitive_nth_root(N), N)
+            self.b = [mpoly(W, 3), mpoly(W, 1), multivariate.MPolynomial(dict())]
+            self.t = [mpoly(2 * W, 6), mpoly(2 * W, 2)]
+            self.e = [mpoly(W, 4)]
+
+        def boundary_constraints_ext(self, challenges):
+            return self.b
+
+        def transition_constraints_ext(self, challenges):
+            return self.t
+
+        def terminal_constraints_ext(self, challenges, terminals):
+            return self.e
+
+    tables = [Toy(5), Toy(0)]
+    for t in tables:
+        t.codewords = [[rx() for _ in range(N)] for _ in range(W)]
+        t.codewords[1][3] = xf.zero()
+        t.codewords[2][7] = X(11)
+    pa = permutation_argument.PermutationArgument(tables, (0, 1), (1, 2))
+
+    def run():
+        out = []
+        for t in tables:
+            out.append(t.boundary_quotients(dom, t.codewords, None))
+            out.append(t.transition_quotients(dom, t.codewords, None))
+            out.append(t.terminal_quotients(dom, t.codewords, None, None))
+        out.append([pa.quotient(dom)])
+        return out
+
+    eng = reference_dropin.engine
+    launches0 = eng.launch_count()
+    got = run()
+    assert eng.launch_count() > launches0
+    dropin.uninstall()
+    try:
+        want = run()
+    finally:
+        dropin.install(REFERENCE_DIR, engine=eng)
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for gc, wc in zip(g, w):
+            assert [[c.value for c in x.polynomial.coefficients] for x in gc] == \
+                   [[c.value for c in x.polynomial.coefficients] for x in wc]
+            assert pickle.dumps(gc) == pickle.dumps(wc)

@@ -1,0 +1,26 @@
+"""BASELINE config 5 at the scale the reference can finish: the UNMODIFIED
+brainfuck_stark.BrainfuckStark.prove("++++") with the drop-in installed -- hot path and quotient
+codewords through the C-ABI surface (host-memory test backend here; the GPU box has no reference
+checkout) -- must produce a proof that the reference's own verifier accepts and that is byte-identical
+to the all-reference proof recorded in tests/golden/bfs.json (seeded urandom)."""
+import os
+import subprocess
+import sys
+import json
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE_DIR = os.environ.get("B2S_REFERENCE_DIR", "/root/reference/code")
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference checkout not available")
+def test_prove_under_dropin_is_byte_identical_and_accepted(tmp_path):
+    out = str(tmp_path / "res.json")
+    # own process: prove() patches os.urandom and imports the reference's modules by bare name
+    subprocess.check_call([sys.executable, os.path.join(HERE, "e2e_prove_dropin.py"), "fake", out],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    res = json.load(open(out))
+    assert res["reference_verifier_accepts"] is True
+    assert res["byte_identical_to_reference_proof"] is True
+    assert res["fri_domain_length"] == 1024 and res["engine_calls_launching_kernels"] > 0

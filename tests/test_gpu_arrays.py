@@ -261,3 +261,43 @@ def test_launch_counter_moves(eng):
     a = eng.launch_count()
     eng.ntt(eng.upload(rand_bfe(1, 64)), 6, root_of_unity(6))
     assert eng.launch_count() > a
+
+
+def test_quotients_golden_and_oracle(eng):
+    """SURVEY 8(f) row 1 through the C ABI: the reference's golden quotient codewords, then random programs
+    at larger domains against the oracle, and the vanishing-zerofier flag."""
+    from util import quotient_cases
+    g = golden("quotients.json")
+    for name, cw, shift, prog, kind, height, oinv, want in quotient_cases(g):
+        W, _, N = cw.shape
+        d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
+        out, vanishes = eng.quotients(d, shift, *prog, kind, height, oinv, g["offset"], g["omega"])
+        assert not vanishes, name
+        assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), want), name
+    R = random.Random(77)
+    for logn, W, ncons in ((10, 5, 4), (14, 11, 3)):
+        N = 1 << logn
+        cw = np.stack([rand_xfe(500 + logn + j, N) for j in range(W)])
+        program = []
+        for _ in range(ncons):
+            cons = []
+            for _ in range(R.randrange(1, 12)):
+                k = [0] * (2 * W)
+                for _ in range(R.randrange(0, 5)):
+                    k[R.randrange(2 * W)] += R.randrange(1, 9)
+                cons.append([k, [R.randrange(P) for _ in range(3)]])
+            program.append(cons)
+        from util import quotient_program
+        prog = quotient_program(program)
+        d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
+        for kind, height in ((2, 8), (2, 0)):
+            oinv = pow(root_of_unity(3), P - 2, P)
+            out, vanishes = eng.quotients(d, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
+            ref, rv = orc.quotients(cw, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
+            assert vanishes == rv is False
+            assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref)
+    # offset 1 puts x = 1 on the domain: boundary zerofier vanishes
+    name, cw, shift, prog, kind, height, oinv, want = next(iter(quotient_cases(g)))
+    W, _, N = cw.shape
+    _, vanishes = eng.quotients(eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N), 0, *prog, 1, 0, 1, 1, g["omega"])
+    assert vanishes

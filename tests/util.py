@@ -47,3 +47,37 @@ def root_of_unity(log_n):
     for _ in range(32 - log_n):
         r = r * r % P
     return r
+
+
+def quotient_program(program):
+    """tests/golden/quotients.json `program` ([[exponent vector, coefficient triple], ...] per constraint)
+    -> (mono_off, coeffs, factors) arrays of b2s_quotients / orc_quotients"""
+    mono_off, coeffs, facs = [0], [], []
+    for constraint in program:
+        for k, c in constraint:
+            coeffs.append(c)
+            facs.append([(i << 8) | e for i, e in enumerate(k) if e])
+        mono_off.append(len(coeffs))
+    width = max([len(f) for f in facs] + [1])
+    factors = np.zeros((len(facs), width), dtype=np.uint32)
+    for m, f in enumerate(facs):
+        factors[m, :len(f)] = f
+    return (np.asarray(mono_off, dtype=np.uint32), np.asarray(coeffs, dtype=np.uint64).reshape(-1, 3), factors)
+
+
+def quotient_cases(g):
+    """(name, cw (W,3,N), shift, program arrays, kind, height, omicron_inv, expected (C,3,N)) per golden case"""
+    N, W = g["N"], g["width"]
+    for ti, t in enumerate(g["tables"]):
+        cw = np.array(t["codewords"], dtype=np.uint64).transpose(0, 2, 1).copy()
+        for kind, name in ((1, "boundary"), (2, "transition"), (3, "terminal")):
+            e = t[name]
+            want = np.array(e["out"], dtype=np.uint64).reshape(-1, N, 3).transpose(0, 2, 1)
+            yield ("table%d_%s" % (ti, name), cw, t["unit_distance"] if kind == 2 else 0, quotient_program(e["program"]),
+                   kind, t["height"], t["omicron_inv"], want)
+    pm = g["permutation"]
+    lhs = np.array(g["tables"][pm["lhs"][0]]["codewords"][pm["lhs"][1]], dtype=np.uint64).T
+    rhs = np.array(g["tables"][pm["rhs"][0]]["codewords"][pm["rhs"][1]], dtype=np.uint64).T
+    prog = quotient_program([[[[1, 0], [1, 0, 0]], [[0, 1], [P - 1, 0, 0]]]])
+    yield ("permutation", np.stack([lhs, rhs]).copy(), 0, prog, 1, 0, 1,
+           np.array(pm["out"], dtype=np.uint64).T.reshape(1, 3, N))
