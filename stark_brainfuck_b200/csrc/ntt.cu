@@ -151,6 +151,61 @@ int get_table(const Tab4 &t, cudaStream_t st, const u64 **out) {
     return 0;
 }
 
+struct PlanKey {
+    u64 w, scale, n_in;
+    u32 log_n, flags;
+    int dev;
+    bool operator<(const PlanKey &o) const {
+        if (w != o.w) return w < o.w;
+        if (scale != o.scale) return scale < o.scale;
+        if (n_in != o.n_in) return n_in < o.n_in;
+        if (log_n != o.log_n) return log_n < o.log_n;
+        if (flags != o.flags) return flags < o.flags;
+        return dev < o.dev;
+    }
+};
+struct CachedPlan {
+    Pass4Plan plan[3];
+    int npass;
+};
+std::mutex g_plan_mu;
+std::map<PlanKey, CachedPlan> g_plans;
+
+// 4 columns per tile = full 32-byte sectors (narrower tiles balance a single 2^20 vector better
+// over 148 SMs but measured slower: profiles/r01_ntt_experiments.md)
+int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale, cudaStream_t st, Pass4Plan plan[3],
+             int *npass) {
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    const PlanKey key{w, do_scale ? scale : 1, n_in, log_n, (inverse ? 1u : 0u) | (do_scale ? 2u : 0u), dev};
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it == g_plans.end()) {
+        if (g_plans.size() > 4096) g_plans.clear();  // bounded: callers with ever-changing roots
+        CachedPlan cp;
+        cp.npass = plan4(log_n, n_in, w, scale, inverse, do_scale, 2, cp.plan);
+        int rc = 0;
+        for (int ps = 0; ps < cp.npass; ++ps) {
+            Pass4Plan &pl = cp.plan[ps];
+            auto bind = [&](const Tab4 &t, const u64 *&dst) {
+                if (t.used && rc == 0) rc = get_table(t, st, &dst);
+            };
+            bind(pl.tw_tail, pl.P.tw_tail);
+            bind(pl.tw_core, pl.P.tw_core);
+            bind(pl.in_scale, pl.P.in_scale);
+            bind(pl.out_scale, pl.P.out_scale);
+            bind(pl.tw_lo, pl.P.tw_lo);
+            bind(pl.tw_hi, pl.P.tw_hi);
+            bind(pl.col_scale, pl.P.col_scale);
+        }
+        if (rc) return rc;
+        it = g_plans.emplace(key, cp).first;
+    }
+    for (int ps = 0; ps < 3; ++ps) plan[ps] = it->second.plan[ps];  // copied under the lock
+    *npass = it->second.npass;
+    return 0;
+}
+
 template <int TL>
 int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     const Pass4Params &P = pl.P;
@@ -192,6 +247,10 @@ int dispatch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
 }  // namespace
 
 void ntt_cache_clear() {
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        g_plans.clear();
+    }
     std::lock_guard<std::mutex> lk(g_tab_mu);
     for (auto &kv : g_tab) {
         cudaFree(kv.second.ptr);
@@ -247,26 +306,16 @@ int ntt_run(const u64 *d_in, u64 in_stride, u32 n_in, u64 *d_out, u64 out_stride
         return 0;
     }
 
+    // plans (digit split, strides, constant twiddles, table pointers) are cached per transform
+    // shape: building one costs ~15 us of host arithmetic, as much as a small transform on the device
     Pass4Plan plan[3];
-    // 4 columns per tile = full 32-byte sectors (narrower tiles balance a single 2^20 vector
-    // better over 148 SMs but measured slower: profiles/r01_ntt_experiments.md)
-    const int npass = plan4(log_n, n_in, w, scale, inverse != 0, do_scale, 2, plan);
+    int npass = 0;
+    int rc = get_plan(log_n, n_in, w, scale, inverse != 0, do_scale, st, plan, &npass);
+    if (rc) return rc;
     u64 *work = nullptr;
     if (npass > 1) B2S_CUDA(cudaMallocAsync(&work, sizeof(u64) * n * n_planes, st));
-    int rc = 0;
     for (int ps = 0; ps < npass && rc == 0; ++ps) {
         Pass4Plan &pl = plan[ps];
-        auto bind = [&](const Tab4 &t, const u64 *&dst) {
-            if (t.used && rc == 0) rc = get_table(t, st, &dst);
-        };
-        bind(pl.tw_tail, pl.P.tw_tail);
-        bind(pl.tw_core, pl.P.tw_core);
-        bind(pl.in_scale, pl.P.in_scale);
-        bind(pl.out_scale, pl.P.out_scale);
-        bind(pl.tw_lo, pl.P.tw_lo);
-        bind(pl.tw_hi, pl.P.tw_hi);
-        bind(pl.col_scale, pl.P.col_scale);
-        if (rc) break;
         pl.P.in = pl.first ? d_in : work;
         pl.P.in_plane_stride = pl.first ? in_stride : n;
         pl.P.out = pl.last ? d_out : work;
