@@ -151,6 +151,8 @@ GL_HD void pass4_tail(const Pass4Params &P, const u32 tid, const u32 nthreads, c
     // arithmetic, so a pass pays one global-memory round trip, not NG of them.
     constexpr int NG = 16 >> TL;
     u64 v[NG][M];
+    u32 idx0[NG];
+    const bool full = (u32)NG * nthreads == ngroups;  // false only for tiles smaller than one warp's worth
 #pragma unroll
     for (int gi = 0; gi < NG; ++gi) {
         const u32 g = tid + (u32)gi * nthreads;
@@ -162,14 +164,30 @@ GL_HD void pass4_tail(const Pass4Params &P, const u32 tid, const u32 nthreads, c
             col = g & (T - 1);
             low = g >> P.log_T;
         }
-        const u32 idx0 = blk0 + col * cst + low * rs;
+        idx0[gi] = g < ngroups ? blk0 + col * cst + low * rs : 0;  // groups past the tile read element 0
+    }
+    if (full && !check) {
 #pragma unroll
-        for (int j = 0; j < M; ++j) {
-            const u32 idx = idx0 + (u32)bitrev4_c(j, TL) * Lrs;
-            const bool ok = g < ngroups && (!check || idx < n_in);
-            const u64 x = plane0[ok ? idx : 0];  // n_in == 0 never launches
-            v[gi][j] = ok ? x : 0;
-        }
+        for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+            for (int j = 0; j < M; ++j) v[gi][j] = plane0[idx0[gi] + (u32)bitrev4_c(j, TL) * Lrs];
+    } else {
+        // zero padding beyond n_in (code/fri.py:28-29): clamp the address, then clear by index
+        const u32 last = check ? n_in - 1 : 0xFFFFFFFFu;  // n_in == 0 never launches
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const u32 idx = idx0[gi] + (u32)bitrev4_c(j, TL) * Lrs;
+                v[gi][j] = plane0[idx < last ? idx : last];
+            }
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                const u32 idx = idx0[gi] + (u32)bitrev4_c(j, TL) * Lrs;
+                if (idx > last || tid + (u32)gi * nthreads >= ngroups) v[gi][j] = 0;
+            }
     }
     bool waited = false;
 #pragma unroll
