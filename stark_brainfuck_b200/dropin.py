@@ -33,10 +33,11 @@ def current_glue():
     return _state["glue"] if _state else None
 
 
-def install(reference_dir=None, engine=None, quotients=True):
+def install(reference_dir=None, engine=None, quotients=True, salted=True):
     """Patch the reference modules importable from `reference_dir` (or already on sys.path).
     `quotients=True` also moves the quotient-codeword loops of table.py / permutation_argument.py
-    (93 % of prove()) to the device.  Returns the Glue in use."""
+    (93 % of prove()) to the device, `salted=True` the trees of salted_merkle.py.
+    Returns the Glue in use."""
     global _state
     if _state is not None:
         return _state["glue"]
@@ -105,6 +106,13 @@ def install(reference_dir=None, engine=None, quotients=True):
                  else glue.table_terminal_quotients(self, domain, codewords, challenges, terminals))
         set_attr(pa.PermutationArgument, "quotient", lambda self, fri_domain:
                  orig_q(self, fri_domain) if debug() else glue.permutation_quotient(self, fri_domain, mv.MPolynomial))
+
+    # -- 5. next row: SaltedMerkle (two of the three trees of prove()) -----------
+    if salted:
+        sm = importlib.import_module("salted_merkle")
+        # `urandom` is looked up in the module at call time: tests patch salted_merkle.urandom
+        set_attr(sm.SaltedMerkle, "__init__",
+                 lambda self, data_array: glue.salted_merkle_build(self, data_array, lambda k: sm.urandom(k)))
 
     _state = {"glue": glue, "saved": saved, "mods": mods}
     return glue

@@ -378,6 +378,25 @@ class Glue:
         """code/merkle.py:46-52"""
         return tree.nodes.open(index, tree.depth)
 
+    def salted_merkle_build(self, tree, data_array, urandom):
+        """Body of SaltedMerkle.__init__ (code/salted_merkle.py:8-46): leaf i =
+        blake2b(pickle(element) | pickle(salt)), salts drawn with the caller's `urandom` in leaf order.
+        The leaves are tuples whose elements carry different field objects, so the host
+        pickles them and the device hashes the byte strings and builds the tree (b2s_merkle_blobs).
+        open / verify / root stay the reference's: they only index .leafs and .nodes."""
+        n = len(data_array)
+        tree.num_leafs = n
+        npo2 = 1
+        while npo2 < n:
+            npo2 <<= 1
+        tree.depth = _ilog2(npo2)  # code/salted_merkle.py:10-22 (0 leaves -> depth 0 as well)
+        tree.leafs = [(element, urandom(24)) for element in data_array]  # code/salted_merkle.py:25
+        # code/salted_merkle.py:23: with no leaves the reference's own consistency assert fires
+        assert n != 0, "in SaltedMerkle.__init__, next_power_of_two = 0 =/= 1 << self.depth = 1"
+        dumps = pickle.dumps
+        tree._device_nodes = self.engine.merkle_blobs([dumps(e) + dumps(salt) for e, salt in tree.leafs])
+        tree.nodes = NodeView(self.engine, tree._device_nodes, npo2, n)
+
     # ------------------------------------------------------------------ code/fri.py Fri
     def fri_commit(self, fri, codeword, proof_stream, round_index=0, Merkle=None):
         """code/fri.py:91-139.  The round loop stays on the host because each challenge is a

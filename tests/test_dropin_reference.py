@@ -60,7 +60,7 @@ def test_fri_errors(env):
 @pytest.mark.parametrize("modname,funcs", [
     ("test_ntt", ["test_ntt", "test_intt", "test_multiply", "test_divide", "test_interpolate",
                   "test_coset_evaluate", "test_batch_inverse"]),
-    ("test_merkle", ["test_merkle"]),
+    ("test_merkle", ["test_merkle", "test_salted_merkle"]),
     ("test_fri", ["test_fri"]),
 ])
 def test_reference_own_tests_run_unmodified(env, modname, funcs, capsys):
@@ -228,3 +228,51 @@ def test_quotient_codewords_match_reference(reference_dropin):
             assert [[c.value for c in x.polynomial.coefficients] for x in gc] == \
                    [[c.value for c in x.polynomial.coefficients] for x in wc]
             assert pickle.dumps(gc) == pickle.dumps(wc)
+
+
+def test_salted_merkle_matches_reference(reference_dropin):
+    """SaltedMerkle over tuple leaves, seeded salts: same roots, openings and pickles"""
+    import pickle
+    import random
+    from conftest import REFERENCE_DIR
+    from stark_brainfuck_b200 import dropin
+    import algebra
+    import extension_field
+    import salted_merkle
+    import univariate
+    xf = extension_field.ExtensionField.main()
+    bf = xf.modulus.coefficients[0].field
+    f = algebra.BaseField.main()
+    R = random.Random(7)
+    P = 18446744069414584321
+    leaves = {n: [tuple([algebra.BaseFieldElement(R.randrange(P), f) for _ in range(3)] +
+                        [extension_field.ExtensionFieldElement(univariate.Polynomial(
+                            [algebra.BaseFieldElement(R.randrange(P), bf) for _ in range(R.randrange(0, 4))]), xf)])
+                  for _ in range(n)] for n in (1, 5, 64)}
+    old = salted_merkle.urandom
+
+    def run():
+        out = []
+        for n, data in leaves.items():
+            S = random.Random(1000 + n)
+            salted_merkle.urandom = lambda k: bytes(S.getrandbits(8) for _ in range(k))
+            t = salted_merkle.SaltedMerkle(data)
+            opened = [t.open(i) for i in sorted({0, n - 1, n // 2})]
+            for i, (salt, path) in zip(sorted({0, n - 1, n // 2}), opened):
+                assert salted_merkle.SaltedMerkle.verify(t.root(), i, salt, path, data[i])
+            out.append(pickle.dumps((t.root(), opened, t.depth, t.num_leafs, [t.leafs[i] for i in range(n)])))
+        return out
+
+    eng = reference_dropin.engine
+    try:
+        got = run()
+        dropin.uninstall()
+        try:
+            want = run()
+        finally:
+            dropin.install(REFERENCE_DIR, engine=eng)
+    finally:
+        salted_merkle.urandom = old
+    assert got == want
+    with pytest.raises(AssertionError):
+        salted_merkle.SaltedMerkle([])
