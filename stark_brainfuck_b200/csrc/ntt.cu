@@ -24,33 +24,40 @@ namespace {
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
-template <int TL>
-__global__ void __launch_bounds__(512, 2) ntt4_pass_kernel(const __grid_constant__ Pass4Params P) {
+template <int TL, int LE>
+__global__ void __launch_bounds__(LE == 4 ? 512 : 1024, LE == 4 ? 2 : 1)
+    ntt4_pass_kernel(const __grid_constant__ Pass4Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 R = 1u << P.log_R;
-    u64 *tw_tail_s = reinterpret_cast<u64 *>(smem_raw);  // R entries when TL > 0   (TMA destinations,
-    u64 *tw_core_s = tw_tail_s + (TL > 0 ? R : 0);       // 256 entries when a == 2  16-byte aligned)
-    u64 *S = tw_core_s + (P.a == 2 ? 256 : 0);
+    const u32 n_core0 = pass4_core_table_elems(LE, P.a, 0), n_core1 = pass4_core_table_elems(LE, P.a, 1);
+    u64 *tw_tail_s = reinterpret_cast<u64 *>(smem_raw);  // R entries when TL > 0          (TMA destinations,
+    u64 *tw_core_s = tw_tail_s + (TL > 0 ? R : 0);       // tables of core steps 0 .. a-2   16-byte aligned)
+    u64 *S = tw_core_s + n_core0 + n_core1;
     u64 *mbar = S + ((size_t)P.cs << P.log_T);
     const u32 tid = threadIdx.x, nthreads = blockDim.x;
 
     // twiddle tables of this pass: TMA bulk copies, completion on one mbarrier
     const u32 mbar_a = smem_u32(mbar);
-    const u32 bytes_tail = TL > 0 ? R * 8 : 0, bytes_core = P.a == 2 ? 2048 : 0;
+    const u32 bytes_tail = TL > 0 ? R * 8 : 0, bytes0 = n_core0 * 8, bytes1 = n_core1 * 8;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_a));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes_tail + bytes_core)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_a), "r"(bytes_tail + bytes0 + bytes1)
                      : "memory");
         if (bytes_tail)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_u32(tw_tail_s)),
                          "l"(P.tw_tail), "r"(bytes_tail), "r"(mbar_a)
                          : "memory");
-        if (bytes_core)
+        if (bytes0)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                              smem_u32(tw_core_s)),
-                         "l"(P.tw_core), "r"(bytes_core), "r"(mbar_a)
+                         "l"(P.tw_core[0]), "r"(bytes0), "r"(mbar_a)
+                         : "memory");
+        if (bytes1)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(tw_core_s + n_core0)),
+                         "l"(P.tw_core[1]), "r"(bytes1), "r"(mbar_a)
                          : "memory");
     }
     __syncthreads();  // mbarrier initialised
@@ -69,15 +76,15 @@ __global__ void __launch_bounds__(512, 2) ntt4_pass_kernel(const __grid_constant
             "}\n" ::"r"(mbar_a)
             : "memory");
     };
-    pass4_tail<TL>(P, tid, nthreads, blockIdx.x, blockIdx.y, blockIdx.z, tw_tail_s, S, tables_ready);
+    pass4_tail<TL, LE>(P, tid, nthreads, blockIdx.x, blockIdx.y, blockIdx.z, tw_tail_s, S, tables_ready);
     __syncthreads();
     for (u32 s = 0; s < P.a; ++s) {
-        pass4_core(P, s, tid, nthreads, tw_core_s, S);
+        pass4_core<LE>(P, s, tid, nthreads, tw_core_s, S);
         if (s + 1 < P.a) __syncthreads();
     }
     asm volatile("griddepcontrol.launch_dependents;");
     // the out phase reads back exactly what this thread wrote in the last core step
-    pass4_out(P, tid, nthreads, blockIdx.x, blockIdx.y, blockIdx.z, S);
+    pass4_out<LE>(P, tid, nthreads, blockIdx.x, blockIdx.y, blockIdx.z, S);
 }
 
 // tab[i] = Montgomery form of base^i (kind 1) or of base^((i >> log_l) * (i mod 2^log_l)) (kind 2:
@@ -153,7 +160,7 @@ int get_table(const Tab4 &t, cudaStream_t st, const u64 **out) {
 
 struct PlanKey {
     u64 w, scale, n_in;
-    u32 log_n, flags;
+    u32 log_n, flags;  // flags: inverse, do_scale, log_E
     int dev;
     bool operator<(const PlanKey &o) const {
         if (w != o.w) return w < o.w;
@@ -173,17 +180,17 @@ std::map<PlanKey, CachedPlan> g_plans;
 
 // 4 columns per tile = full 32-byte sectors (narrower tiles balance a single 2^20 vector better
 // over 148 SMs but measured slower: profiles/r01_ntt_experiments.md)
-int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale, cudaStream_t st, Pass4Plan plan[3],
-             int *npass) {
+int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale, u32 log_E, cudaStream_t st,
+             Pass4Plan plan[3], int *npass) {
     int dev = 0;
     B2S_CUDA(cudaGetDevice(&dev));
-    const PlanKey key{w, do_scale ? scale : 1, n_in, log_n, (inverse ? 1u : 0u) | (do_scale ? 2u : 0u), dev};
+    const PlanKey key{w, do_scale ? scale : 1, n_in, log_n, (inverse ? 1u : 0u) | (do_scale ? 2u : 0u) | (log_E << 2), dev};
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         if (g_plans.size() > 4096) g_plans.clear();  // bounded: callers with ever-changing roots
         CachedPlan cp;
-        cp.npass = plan4(log_n, n_in, w, scale, inverse, do_scale, 2, cp.plan);
+        cp.npass = plan4(log_n, n_in, w, scale, inverse, do_scale, 2, log_E, cp.plan);
         int rc = 0;
         for (int ps = 0; ps < cp.npass; ++ps) {
             Pass4Plan &pl = cp.plan[ps];
@@ -191,7 +198,8 @@ int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale,
                 if (t.used && rc == 0) rc = get_table(t, st, &dst);
             };
             bind(pl.tw_tail, pl.P.tw_tail);
-            bind(pl.tw_core, pl.P.tw_core);
+            bind(pl.tw_core[0], pl.P.tw_core[0]);
+            bind(pl.tw_core[1], pl.P.tw_core[1]);
             bind(pl.in_scale, pl.P.in_scale);
             bind(pl.out_scale, pl.P.out_scale);
             bind(pl.tw_lo, pl.P.tw_lo);
@@ -206,21 +214,21 @@ int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale,
     return 0;
 }
 
-template <int TL>
+template <int TL, int LE>
 int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     const Pass4Params &P = pl.P;
-    const size_t smem = sizeof(u64) * ((TL > 0 ? ((size_t)1 << P.log_R) : 0) + (P.a == 2 ? 256 : 0) +
-                                       pass4_smem_elems(P.log_R, P.log_T)) + 16;
+    const size_t smem = sizeof(u64) * ((TL > 0 ? ((size_t)1 << P.log_R) : 0) + pass4_core_table_elems(LE, P.a, 0) +
+                                       pass4_core_table_elems(LE, P.a, 1) + pass4_smem_elems(P.log_R, P.log_T, LE)) + 16;
     static size_t attr_done[16] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_done[dev & 15] < smem) {
-        B2S_CUDA(cudaFuncSetAttribute(ntt4_pass_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2S_CUDA(cudaFuncSetAttribute(ntt4_pass_kernel<TL, LE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done[dev & 15] = smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid_x, pl.grid_y, n_planes);
-    cfg.blockDim = dim3(pass4_threads(P.log_R, P.log_T));
+    cfg.blockDim = dim3(pass4_threads(P.log_R, P.log_T, LE));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -228,19 +236,27 @@ int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pl.first ? 0 : 1;  // the first pass depends on whatever the caller enqueued before
-    B2S_CUDA(cudaLaunchKernelEx(&cfg, ntt4_pass_kernel<TL>, P));
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, ntt4_pass_kernel<TL, LE>, P));
     B2S_LAUNCHED();
     return 0;
 }
 
 int dispatch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
-    switch (pl.tail) {
-        case 0: return launch_pass4<0>(pl, n_planes, st);
-        case 1: return launch_pass4<1>(pl, n_planes, st);
-        case 2: return launch_pass4<2>(pl, n_planes, st);
-        case 3: return launch_pass4<3>(pl, n_planes, st);
+    if (pl.P.log_E == 4) {
+        switch (pl.tail) {
+            case 0: return launch_pass4<0, 4>(pl, n_planes, st);
+            case 1: return launch_pass4<1, 4>(pl, n_planes, st);
+            case 2: return launch_pass4<2, 4>(pl, n_planes, st);
+            case 3: return launch_pass4<3, 4>(pl, n_planes, st);
+        }
+    } else if (pl.P.log_E == 3) {
+        switch (pl.tail) {
+            case 0: return launch_pass4<0, 3>(pl, n_planes, st);
+            case 1: return launch_pass4<1, 3>(pl, n_planes, st);
+            case 2: return launch_pass4<2, 3>(pl, n_planes, st);
+        }
     }
-    b2s_set_error("unsupported tail radix 2^%u", pl.tail);
+    b2s_set_error("unsupported pass shape: tail 2^%u, core 2^%u", pl.tail, pl.P.log_E);
     return B2S_ERR_ARG;
 }
 
@@ -310,7 +326,12 @@ int ntt_run(const u64 *d_in, u64 in_stride, u32 n_in, u64 *d_out, u64 out_stride
     // shape: building one costs ~15 us of host arithmetic, as much as a small transform on the device
     Pass4Plan plan[3];
     int npass = 0;
-    int rc = get_plan(log_n, n_in, w, scale, inverse != 0, do_scale, st, plan, &npass);
+    // 8-point core steps give a small job twice the threads and half the per-thread chain: faster
+    // up to 2^19 elements in total (2^18: 14.5 vs 18.5 us); 16-point steps need ~20 % fewer
+    // instructions and win once the GPU is full (profiles/r01_ntt_experiments.md)
+    static const char *force_e = getenv("B2S_NTT_LOG_E");
+    const u32 log_E = force_e ? (u32)atoi(force_e) : ((u64)n * n_planes <= ((u64)1 << 19) ? 3 : 4);
+    int rc = get_plan(log_n, n_in, w, scale, inverse != 0, do_scale, log_E, st, plan, &npass);
     if (rc) return rc;
     u64 *work = nullptr;
     if (npass > 1) B2S_CUDA(cudaMallocAsync(&work, sizeof(u64) * n * n_planes, st));

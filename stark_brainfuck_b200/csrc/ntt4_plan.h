@@ -22,7 +22,7 @@ struct Tab4 {
 
 struct Pass4Plan {
     Pass4Params P;  // table pointers, in/out and plane strides are filled in by the caller
-    Tab4 tw_tail, tw_core, in_scale, out_scale, tw_lo, tw_hi, col_scale;
+    Tab4 tw_tail, tw_core[2], in_scale, out_scale, tw_lo, tw_hi, col_scale;
     u32 log_R = 0, log_T = 0, tail = 0;
     bool first = false, last = false;
     u32 grid_x = 1, grid_y = 1;
@@ -32,7 +32,8 @@ static inline bool plan4_supported(u32 log_n) { return log_n >= 4 && log_n <= 30
 
 // w: the root actually used (omega, or omega^-1 for the inverse); scale: offset or offset^-1.
 // Returns the number of passes.
-static inline int plan4(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale, u32 log_T_multi,
+// log_E: 4 = 16-point core steps (fewest instructions), 3 = 8-point core steps (twice the threads).
+static inline int plan4(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale, u32 log_T_multi, u32 log_E,
                         Pass4Plan plan[3]) {
     const u64 n = (u64)1 << log_n;
     u32 lg[3] = {0, 0, 0};
@@ -67,7 +68,7 @@ static inline int plan4(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, boo
         const u32 log_R = lg[ps];
         rest -= log_R;
         const bool first = ps == 0, last = ps + 1 == npass;
-        const u32 a = log_R >= 8 ? 2 : 1, t = log_R - 4 * a;  // R = 2^t * 16^a
+        const u32 a = log_R / log_E, t = log_R - log_E * a;  // R = 2^t * E^a (log_R <= 11: a <= 2 resp. 3)
         pl.log_R = log_R;
         pl.tail = t;
         pl.log_T = npass == 1 ? 0 : LOG_T_MULTI;
@@ -76,13 +77,14 @@ static inline int plan4(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, boo
         P.in = nullptr;
         P.out = nullptr;
         P.in_plane_stride = P.out_plane_stride = 0;
-        P.tw_tail = P.tw_core = P.in_scale = P.out_scale = P.tw_lo = P.tw_hi = P.col_scale = nullptr;
+        P.tw_tail = P.tw_core[0] = P.tw_core[1] = P.in_scale = P.out_scale = P.tw_lo = P.tw_hi = P.col_scale = nullptr;
         P.n_in = n_in;
         P.flags = (first && n_in < n ? P4_FIRST : 0) | (last ? P4_LAST : 0);  // bounds checks only when padding
         P.log_R = log_R;
         P.log_T = pl.log_T;
         P.a = a;
-        P.cs = pass4_cs(log_R, pl.log_T);
+        P.log_E = log_E;
+        P.cs = pass4_cs(log_R, pl.log_T, log_E);
         P.out_mul = GL_EPS;  // 1
         for (int b = 0; b < 32; ++b) P.s_sq[b] = s_sq[b];
         const u64 wR = gl_pow(w, n >> log_R);  // primitive R-th root
@@ -95,12 +97,13 @@ static inline int plan4(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, boo
             pl.tw_tail.log_count = log_R;
             pl.tw_tail.log_r2 = log_R - t;
         }
-        if (a == 2) {  // w_256^(k * lo), k, lo < 16
-            pl.tw_core.used = true;
-            pl.tw_core.two_d = true;
-            pl.tw_core.base = gl_pow(wR, (u64)1 << t);
-            pl.tw_core.log_count = 8;
-            pl.tw_core.log_r2 = 4;
+        for (u32 st = 0; st + 1 < a; ++st) {  // core step st: w_M^(k * lo), k < E, lo < L = E^(a-1-st), M = E L
+            const u32 log_M = log_E * (a - st);
+            pl.tw_core[st].used = true;
+            pl.tw_core[st].two_d = true;
+            pl.tw_core[st].base = gl_pow(wR, (u64)1 << (log_R - log_M));
+            pl.tw_core[st].log_count = log_M;
+            pl.tw_core[st].log_r2 = log_M - log_E;
         }
         if (!last) {
             const u64 ncols = (u64)1 << rest;

@@ -37,28 +37,41 @@ static std::vector<u64> build_table(const Tab4 &t) {
     return tab;
 }
 
-template <int TL>
+template <int TL, int LE>
 static void emulate_pass(const Pass4Plan &pl, u32 n_planes) {
     const Pass4Params &P = pl.P;
-    const u32 nthreads = pass4_threads(P.log_R, P.log_T);
-    std::vector<u64> S(pass4_smem_elems(P.log_R, P.log_T));
+    const u32 nthreads = pass4_threads(P.log_R, P.log_T, LE);
+    std::vector<u64> S(pass4_smem_elems(P.log_R, P.log_T, LE));
+    // the TMA bulk copies: tables of the core steps back to back
+    std::vector<u64> core;
+    for (u32 st = 0; st < 2; ++st)
+        if (pass4_core_table_elems(LE, P.a, st)) core.insert(core.end(), P.tw_core[st], P.tw_core[st] + pass4_core_table_elems(LE, P.a, st));
     for (u32 bz = 0; bz < n_planes; ++bz)
         for (u32 by = 0; by < pl.grid_y; ++by)
             for (u32 bx = 0; bx < pl.grid_x; ++bx) {
                 for (auto &x : S) x = 0xDEADBEEFDEADBEEFULL;
-                for (u32 t = 0; t < nthreads; ++t) pass4_tail<TL>(P, t, nthreads, bx, by, bz, P.tw_tail, S.data(), [] {});
+                for (u32 t = 0; t < nthreads; ++t)
+                    pass4_tail<TL, LE>(P, t, nthreads, bx, by, bz, P.tw_tail, S.data(), [] {});
                 for (u32 s = 0; s < P.a; ++s)
-                    for (u32 t = 0; t < nthreads; ++t) pass4_core(P, s, t, nthreads, P.tw_core, S.data());
-                for (u32 t = 0; t < nthreads; ++t) pass4_out(P, t, nthreads, bx, by, bz, S.data());
+                    for (u32 t = 0; t < nthreads; ++t) pass4_core<LE>(P, s, t, nthreads, core.data(), S.data());
+                for (u32 t = 0; t < nthreads; ++t) pass4_out<LE>(P, t, nthreads, bx, by, bz, S.data());
             }
 }
 
 static int dispatch(const Pass4Plan &pl, u32 n_planes) {
-    switch (pl.tail) {
-        case 0: emulate_pass<0>(pl, n_planes); return 0;
-        case 1: emulate_pass<1>(pl, n_planes); return 0;
-        case 2: emulate_pass<2>(pl, n_planes); return 0;
-        case 3: emulate_pass<3>(pl, n_planes); return 0;
+    if (pl.P.log_E == 4) {
+        switch (pl.tail) {
+            case 0: emulate_pass<0, 4>(pl, n_planes); return 0;
+            case 1: emulate_pass<1, 4>(pl, n_planes); return 0;
+            case 2: emulate_pass<2, 4>(pl, n_planes); return 0;
+            case 3: emulate_pass<3, 4>(pl, n_planes); return 0;
+        }
+    } else {
+        switch (pl.tail) {
+            case 0: emulate_pass<0, 3>(pl, n_planes); return 0;
+            case 1: emulate_pass<1, 3>(pl, n_planes); return 0;
+            case 2: emulate_pass<2, 3>(pl, n_planes); return 0;
+        }
     }
     return -1;
 }
@@ -71,14 +84,14 @@ static u64 rnd() {
     return rng_state;
 }
 
-static int run_case(u32 log_n, u64 n_in, u64 offset, bool inverse, u32 n_planes, u32 log_T = 2) {
+static int run_case(u32 log_n, u64 n_in, u64 offset, bool inverse, u32 n_planes, u32 log_T = 2, u32 log_E = 4) {
     const u64 n = (u64)1 << log_n;
     u64 omega = 1753635133440165772ULL;  // code/algebra.py:129
     for (u32 i = 0; i < 32 - log_n; ++i) omega = gl_mul(omega, omega);
     const u64 w = inverse ? gl_inv(omega) : omega;
     const u64 scale = inverse ? gl_inv(offset) : offset;
     Pass4Plan plan[3];
-    const int npass = plan4(log_n, n_in, w, scale, inverse, offset != 1, log_T, plan);
+    const int npass = plan4(log_n, n_in, w, scale, inverse, offset != 1, log_T, log_E, plan);
 
     std::vector<u64> in(n_in * n_planes), out(n * n_planes, 0x1111111111111111ULL), work(n * n_planes, 0x2222);
     for (auto &x : in) {
@@ -95,7 +108,8 @@ static int run_case(u32 log_n, u64 n_in, u64 offset, bool inverse, u32 n_planes,
             dst = keep.back().data();
         };
         bind(pl.tw_tail, pl.P.tw_tail);
-        bind(pl.tw_core, pl.P.tw_core);
+        bind(pl.tw_core[0], pl.P.tw_core[0]);
+        bind(pl.tw_core[1], pl.P.tw_core[1]);
         bind(pl.in_scale, pl.P.in_scale);
         bind(pl.out_scale, pl.P.out_scale);
         bind(pl.tw_lo, pl.P.tw_lo);
@@ -145,6 +159,8 @@ int main(int argc, char **argv) {
                     if (inverse && n_in != n) continue;
                     ++cases;
                     fails += run_case(log_n, n_in, offset, inverse != 0, log_n <= 12 ? 2 : 1);
+                    ++cases;  // 8-point core steps (small batches)
+                    fails += run_case(log_n, n_in, offset, inverse != 0, log_n <= 12 ? 2 : 1, 2, 3);
                     if (log_n >= 12 && n_in == n) {  // narrower tiles (used for small batches)
                         cases += 2;
                         fails += run_case(log_n, n_in, offset, inverse != 0, 1, 0);
