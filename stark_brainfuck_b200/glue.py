@@ -561,9 +561,11 @@ class DeviceCodeword:
             a = self._glue.engine.download(self._planes)
             mk, xf = self._glue.B.make_xfe, self._xfield
             c0, c1, c2 = a[0].tolist(), a[1].tolist(), a[2].tolist()
-            for i in range(self._n):
-                if i not in self._cache:
-                    self._cache[i] = mk(c0[i], c1[i], c2[i], xf)
+            from .marshal import bulk_allocation
+            with bulk_allocation():
+                for i in range(self._n):
+                    if i not in self._cache:
+                        self._cache[i] = mk(c0[i], c1[i], c2[i], xf)
         return [self._cache[i] for i in range(self._n)]
 
     def __eq__(self, other):

@@ -11,7 +11,9 @@ order and the same shared `field` objects the reference's arithmetic would have 
 Objects are built with cls.__new__ + __dict__ in the constructor's attribute order, which
 pickles byte-identically to objects built by __init__.
 """
+import contextlib
 import ctypes as C
+import gc
 import pickle
 
 import numpy as np
@@ -19,6 +21,20 @@ import numpy as np
 from ._lib import TPL_MAX_BYTES, LeafTemplates
 
 P = 18446744069414584321
+
+
+@contextlib.contextmanager
+def bulk_allocation():
+    """Building millions of small container objects with the cyclic collector enabled costs ~10x:
+    every generation-0 overflow rescans the growing heap (measured: 10.1 -> 1.1 us per
+    ExtensionFieldElement).  Nothing built here is cyclic, so the collector is paused."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class Binding:
@@ -102,10 +118,11 @@ class Binding:
         B = self.BaseFieldElement
         new = B.__new__
         out = []
-        for v in arr.tolist():
-            o = new(B)
-            o.__dict__ = {"value": v, "field": field}
-            out.append(o)
+        with bulk_allocation():
+            for v in arr.tolist():
+                o = new(B)
+                o.__dict__ = {"value": v, "field": field}
+                out.append(o)
         return out
 
     def make_xfe(self, c0, c1, c2, xfield, bf=None):
@@ -129,7 +146,27 @@ class Binding:
     def np_to_xfe(self, planes, xfield):
         bf = self.inner_field(xfield)
         mk = self.make_xfe
-        return [mk(a, b, c, xfield, bf) for a, b, c in zip(planes[0].tolist(), planes[1].tolist(), planes[2].tolist())]
+        B, Pn, X = self.BaseFieldElement, self.Polynomial, self.ExtensionFieldElement
+        nB, nP, nX = B.__new__, Pn.__new__, X.__new__
+        out = []
+        app = out.append
+        with bulk_allocation():
+            for a, b, c in zip(planes[0].tolist(), planes[1].tolist(), planes[2].tolist()):
+                if c:  # the common case spelled out: three coefficients, nothing to trim
+                    o0 = nB(B)
+                    o0.__dict__ = {"value": a, "field": bf}
+                    o1 = nB(B)
+                    o1.__dict__ = {"value": b, "field": bf}
+                    o2 = nB(B)
+                    o2.__dict__ = {"value": c, "field": bf}
+                    p = nP(Pn)
+                    p.__dict__ = {"coefficients": [o0, o1, o2]}
+                    x = nX(X)
+                    x.__dict__ = {"polynomial": p, "field": xfield}
+                    app(x)
+                else:
+                    app(mk(a, b, c, xfield, bf))
+        return out
 
     # ---- leaf templates -----------------------------------------------------------
     def xfe_templates(self, xfield):
