@@ -1,3 +1,4 @@
+"""One transform vs a batch of the same total size; host time per call.  Run on the GPU box."""
 import os, sys
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import torch
@@ -12,7 +13,7 @@ for lg in (18, 20):
     xb = torch.randint(0, 2 ** 62, ((32 << 20) >> lg, n), dtype=torch.int64, device=eng.device); yb = torch.empty_like(xb)
     eng.ntt(xb, lg, w, out=yb)
     msb, _ = eng.ntt_timed(xb, lg, w, out=yb, iters=5)
-    print("3pass=%s 2^%d single (warm L2) %.2f us; batched 2^25 elements %.1f us" % (os.environ.get("B2S_EXP_3PASS"), lg, ms * 1e3, msb * 1e3))
+    print("2^%d: one vector (warm L2, 20 back-to-back calls) %.2f us; 2^25 elements in one call %.1f us" % (lg, ms * 1e3, msb * 1e3))
 import time
 lg = 20; n = 1 << lg; w = root_of_unity(lg)
 x = eng.upload(rand_bfe(1, n)); y = eng.empty(1, n)

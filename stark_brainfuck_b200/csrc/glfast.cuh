@@ -1,4 +1,5 @@
-// glfast.cuh -- device-only Goldilocks arithmetic with lazy reduction for the NTT kernels.
+// glfast.cuh -- device-only Goldilocks arithmetic with lazy reduction in the plain (non-Montgomery)
+// domain, for kernels whose twiddles are computed on the fly (dist.cu); the NTT passes use glmont.cuh.
 //
 // Representation: a u64 in [0, 2^64) standing for its residue mod p = 2^64 - 2^32 + 1
 // ("lazy"); a value is "canonical" when it is < p.  2^64 = EPS (mod p), EPS = 2^32 - 1.
