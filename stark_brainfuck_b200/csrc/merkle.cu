@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(LEAF_THREADS)
     __syncthreads();
     const u64 base = (u64)blockIdx.x * LEAF_THREADS;
     const u64 i = base + threadIdx.x;
+    if (nodes && i < 4) reinterpret_cast<ulonglong2 *>(nodes)[i] = make_ulonglong2(0, 0);  // slot 0 is never a node
     const u32 cnt = n < LEAF_THREADS ? (u32)n : LEAF_THREADS;  // leaves of this CTA
     u64 h[8];
     if (threadIdx.x < cnt) {
@@ -360,7 +361,6 @@ int merkle_field_run(const u64 *d_planes, u64 stride, u64 n, const b2s_leaf_temp
     const PreparedLeaf *pl = nullptr;
     int rc = prepare_leaf(tpl, &pl);
     if (rc) return rc;
-    B2S_CUDA(cudaMemsetAsync(d_nodes, 0, 64, st));
     FoldParams F = {};
     if (tpl->n_slots == 3)
         rc = pl->msg_blocks <= 3 ? launch_leaf<3, 3, false>(d_planes, stride, n, pl, F, d_nodes, st)
@@ -432,7 +432,6 @@ extern "C" int b2s_fri_fold(const uint64_t *d_cw, uint64_t cw_stride, uint64_t N
     const PreparedLeaf *pl = nullptr;
     int rc = prepare_leaf(use, &pl);
     if (rc) return rc;
-    if (d_next_nodes) B2S_CUDA(cudaMemsetAsync(d_next_nodes, 0, 64, st));
     return pl->msg_blocks <= 3 ? launch_leaf<3, 3, true>(nullptr, 0, half, pl, F, d_next_nodes, st)
                                : launch_leaf<3, 4, true>(nullptr, 0, half, pl, F, d_next_nodes, st);
 }
