@@ -27,6 +27,7 @@ enum : u32 {
     P4_FIRST = 1,    // bounds check against n_in (zero padding)
     P4_OUT_MUL = 2,  // last pass: multiply the output by out_mul (n^-1)
     P4_LAST = 4,     // last pass of the plan: rows are the contiguous input dimension
+    P4_INPUT = 8,    // first pass of the plan: reads the caller's vector
 };
 
 struct Pass4Params {
@@ -52,6 +53,24 @@ struct Pass4Params {
     u64 w16[8];           // z^e, e < 8, z a primitive 16th root with z^(16/M) = w_M (M = 2, 4, 8, 16)
     // all table entries and out_mul, s_sq, w16 are in Montgomery form (glmont.cuh)
 };
+
+// The caller's input is read once and the final output written once: streaming cache hints keep
+// them from displacing the intermediate vector and the twiddle tables in L2.  The intermediate
+// (written by a non-last pass, read by the next one) uses the default policy and stays resident.
+GL_HD u64 load_stream(const u64 *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcs(reinterpret_cast<const unsigned long long *>(p));
+#else
+    return *p;
+#endif
+}
+GL_HD void store_stream(u64 *p, u64 v) {
+#if defined(__CUDA_ARCH__)
+    __stcs(reinterpret_cast<unsigned long long *>(p), v);
+#else
+    *p = v;
+#endif
+}
 
 GL_HD constexpr int bitrev4_c(int x, int bits) {
     int r = 0;
@@ -175,7 +194,12 @@ GL_HD void pass4_tail(const Pass4Params &P, const u32 tid, const u32 nthreads, c
         }
         idx0[gi] = g < ngroups ? blk0 + col * cst + low * rs : 0;  // groups past the tile read element 0
     }
-    if (full && !check) {
+    if (full && !check && (P.flags & P4_INPUT)) {  // the caller's vector: read once
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi)
+#pragma unroll
+            for (int j = 0; j < M; ++j) v[gi][j] = load_stream(plane0 + idx0[gi] + (u32)bitrev4_c(j, TL) * Lrs);
+    } else if (full && !check) {
 #pragma unroll
         for (int gi = 0; gi < NG; ++gi)
 #pragma unroll
@@ -326,19 +350,19 @@ GL_HD void pass4_out(const Pass4Params &P, const u32 tid, const u32 nthreads, co
             const u64 *os = P.out_scale + kbase;
 #pragma unroll 1
             for (u32 i = 0; i < E; ++i) {
-                out[0] = mont_mul(mont_mul(src[i], cc), os[(u64)i << log_kstride]);
+                store_stream(out, mont_mul(mont_mul(src[i], cc), os[(u64)i << log_kstride]));
                 out += ostep;
             }
         } else if (P.flags & P4_OUT_MUL) {
 #pragma unroll 4
             for (u32 i = 0; i < E; ++i) {
-                out[0] = mont_mul(src[i], P.out_mul);
+                store_stream(out, mont_mul(src[i], P.out_mul));
                 out += ostep;
             }
         } else {
 #pragma unroll 4
             for (u32 i = 0; i < E; ++i) {
-                out[0] = canon4(src[i]);
+                store_stream(out, canon4(src[i]));
                 out += ostep;
             }
         }

@@ -79,7 +79,7 @@ static inline int plan4(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, boo
         P.in_plane_stride = P.out_plane_stride = 0;
         P.tw_tail = P.tw_core[0] = P.tw_core[1] = P.in_scale = P.out_scale = P.tw_lo = P.tw_hi = P.col_scale = nullptr;
         P.n_in = n_in;
-        P.flags = (first && n_in < n ? P4_FIRST : 0) | (last ? P4_LAST : 0);  // bounds checks only when padding
+        P.flags = (first && n_in < n ? P4_FIRST : 0) | (last ? P4_LAST : 0) | (first ? P4_INPUT : 0);  // bounds checks only when padding
         P.log_R = log_R;
         P.log_T = pl.log_T;
         P.a = a;
