@@ -175,6 +175,8 @@ int main(int argc, char **argv) {
         fails += run_case(23, (u64)1 << 21, 7, false, 1);
         ++cases;
         fails += run_case(23, (u64)1 << 23, 7, true, 1);
+        ++cases;  // 8-point core steps: 2^23 = 2^8 * 2^8 * 2^7 with a = 2 and tails 2^2, 2^2, 2^1
+        fails += run_case(23, (u64)1 << 21, 7, false, 1, 2, 3);
     }
     printf("%d cases, %d failed\n", cases, fails);
     return fails ? 1 : 0;

@@ -301,3 +301,33 @@ def test_quotients_golden_and_oracle(eng):
     W, _, N = cw.shape
     _, vanishes = eng.quotients(eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N), 0, *prog, 1, 0, 1, 1, g["omega"])
     assert vanishes
+
+
+@pytest.mark.parametrize("logn", (4, 5, 6, 7, 9, 11, 12, 13, 15))
+def test_ntt_many_planes_16_point_core(eng, logn):
+    """more than 2^19 elements per call select the 16-point core steps also for short transforms
+    (every tail radix and step count of that variant); a few planes are compared with the oracle"""
+    n = 1 << logn
+    q = min((1 << 20) // n, 65535)  # gridDim.z limit; still more than 2^19 elements in total
+    w = root_of_unity(logn)
+    rng = np.random.default_rng(logn)
+    x = rng.integers(0, P, size=(q, n), dtype=np.uint64, endpoint=False)
+    d = eng.upload(x)
+    y = eng.ntt(d, logn, w, offset=7)
+    back = eng.ntt(y, logn, w, offset=7, inverse=True)
+    assert np.array_equal(eng.download(back), x)
+    yh = eng.download(y)
+    for plane in (0, q // 2, q - 1):
+        assert np.array_equal(yh[plane], orc.coset_evaluate(7, w, x[plane], n))
+
+
+def test_ntt_three_pass_plan(eng):
+    """2^23 = 2^8 * 2^8 * 2^7: forward vs oracle, bit-exact round trip"""
+    logn = 23
+    n = 1 << logn
+    x = rand_bfe(23, n)
+    w = root_of_unity(logn)
+    d = eng.upload(x)
+    y = eng.ntt(d, logn, w)
+    assert np.array_equal(eng.download(y)[0], orc.ntt(w, x))
+    assert np.array_equal(eng.download(eng.ntt(y, logn, w, inverse=True))[0], x)
