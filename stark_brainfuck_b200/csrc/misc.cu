@@ -35,50 +35,75 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// code/univariate.py:145-151: value = sum_k c_k * x^k with a running power of the point
+// code/univariate.py:145-151: value = sum_k c_k * x^k.  The reference walks the coefficients with a
+// running power of the point; field arithmetic is exact, so any evaluation order gives the same
+// canonical value.  Here the polynomial is cut into chunks: thread (point q, chunk ch) evaluates its
+// chunk by Horner's rule (lanes of a warp share the coefficient loads), multiplies by x^(first index
+// of the chunk) and a second kernel adds the partial values of a point.
+template <int PP>
+struct EvalAcc;
+template <>
+struct EvalAcc<1> {  // base-field point
+    u64 x;
+    __device__ __forceinline__ void load(const u64 *pts, u64, u64 q) { x = pts[q]; }
+    __device__ __forceinline__ u64 mul(u64 v) const { return gl_mul(v, x); }
+    __device__ __forceinline__ xfe mul(const xfe &v) const { return x_mul_base(v, x); }
+    __device__ __forceinline__ u64 times_power(u64 v, u64 e) const { return gl_mul(v, gl_pow(x, e)); }
+    __device__ __forceinline__ xfe times_power(const xfe &v, u64 e) const { return x_mul_base(v, gl_pow(x, e)); }
+};
+template <>
+struct EvalAcc<3> {  // extension-field point
+    xfe x;
+    __device__ __forceinline__ void load(const u64 *pts, u64 pstride, u64 q) {
+        x = xfe{{pts[q], pts[pstride + q], pts[2 * pstride + q]}};
+    }
+    __device__ __forceinline__ xfe mul(const xfe &v) const { return x_mul(v, x); }
+    __device__ __forceinline__ xfe times_power(const xfe &v, u64 e) const { return x_mul(v, x_pow(x, e)); }
+};
+
 template <int CP, int PP>
 __global__ void __launch_bounds__(128)
-    eval_points_kernel(const u64 *__restrict__ coeffs, u64 cstride, u64 m, const u64 *__restrict__ pts, u64 pstride,
-                       u64 npts, u64 *__restrict__ out, u64 ostride) {
+    eval_chunk_kernel(const u64 *__restrict__ coeffs, u64 cstride, u64 m, const u64 *__restrict__ pts, u64 pstride,
+                      u64 npts, u64 chunk_len, u64 *__restrict__ partial) {
     const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= npts) return;
-    if (CP == 1 && PP == 1) {
-        const u64 x = pts[q];
-        u64 xi = 1, val = 0;
-        for (u64 k = 0; k < m; ++k) {
-            val = gl_add(val, gl_mul(coeffs[k], xi));
-            xi = gl_mul(xi, x);
-        }
-        out[q] = val;
-    } else if (PP == 1) {  // extension coefficients, base-field point
-        const u64 x = pts[q];
-        u64 xi = 1;
-        xfe val = {{0, 0, 0}};
-        for (u64 k = 0; k < m; ++k) {
-            const xfe c = {{coeffs[k], coeffs[cstride + k], coeffs[2 * cstride + k]}};
-            val = x_add(val, x_mul_base(c, xi));
-            xi = gl_mul(xi, x);
-        }
-        out[q] = val.c[0];
-        out[ostride + q] = val.c[1];
-        out[2 * ostride + q] = val.c[2];
+    const u64 k0 = (u64)blockIdx.y * chunk_len;
+    const u64 k1 = k0 + chunk_len < m ? k0 + chunk_len : m;
+    EvalAcc<PP> P;
+    P.load(pts, pstride, q);
+    u64 *dst = partial + (u64)blockIdx.y * 3 * npts + q;
+    if constexpr (CP == 1 && PP == 1) {
+        u64 val = 0;
+        for (u64 k = k1; k-- > k0;) val = gl_add(P.mul(val), coeffs[k]);
+        dst[0] = P.times_power(val, k0);
+        dst[npts] = 0;
+        dst[2 * npts] = 0;
     } else {
-        const xfe x = {{pts[q], pts[pstride + q], pts[2 * pstride + q]}};
-        xfe xi = {{1, 0, 0}}, val = {{0, 0, 0}};
-        for (u64 k = 0; k < m; ++k) {
-            xfe t;
-            if (CP == 1) {
-                t = x_mul_base(xi, coeffs[k]);
-            } else {
-                const xfe c = {{coeffs[k], coeffs[cstride + k], coeffs[2 * cstride + k]}};
-                t = x_mul(c, xi);
+        xfe val = {{0, 0, 0}};
+        for (u64 k = k1; k-- > k0;) {
+            val = P.mul(val);
+            val.c[0] = gl_add(val.c[0], coeffs[k]);
+            if (CP == 3) {
+                val.c[1] = gl_add(val.c[1], coeffs[cstride + k]);
+                val.c[2] = gl_add(val.c[2], coeffs[2 * cstride + k]);
             }
-            val = x_add(val, t);
-            xi = x_mul(xi, x);
         }
-        out[q] = val.c[0];
-        out[ostride + q] = val.c[1];
-        out[2 * ostride + q] = val.c[2];
+        val = P.times_power(val, k0);
+        dst[0] = val.c[0];
+        dst[npts] = val.c[1];
+        dst[2 * npts] = val.c[2];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+    eval_sum_kernel(const u64 *__restrict__ partial, u64 npts, u32 nchunks, u32 out_planes, u64 *__restrict__ out,
+                    u64 ostride) {
+    const u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    for (u32 pl = 0; pl < out_planes; ++pl) {
+        u64 acc = 0;
+        for (u32 ch = 0; ch < nchunks; ++ch) acc = gl_add(acc, partial[((u64)ch * 3 + pl) * npts + q]);
+        out[(u64)pl * ostride + q] = acc;
     }
 }
 
@@ -126,24 +151,43 @@ extern "C" int b2s_eval_points(const uint64_t *d_coeffs, uint64_t coeff_stride, 
                                void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_points == 0) return 0;
+    if ((coeff_planes != 1 && coeff_planes != 3) || (point_planes != 1 && point_planes != 3)) {
+        b2s_set_error("eval_points: planes must be 1 or 3");
+        return B2S_ERR_ARG;
+    }
+    const u32 out_planes = coeff_planes > point_planes ? coeff_planes : point_planes;
+    if (n_coeffs == 0) {  // the zero polynomial
+        B2S_CUDA(cudaMemset2DAsync(d_out, sizeof(u64) * out_stride, 0, sizeof(u64) * n_points, out_planes, st));
+        return 0;
+    }
     const unsigned blocks = (unsigned)((n_points + 127) / 128);
-#define EV(CP, PP)                                                                                              \
-    eval_points_kernel<CP, PP><<<blocks, 128, 0, st>>>(d_coeffs, coeff_stride, n_coeffs, d_points, point_stride, \
-                                                       n_points, d_out, out_stride)
+    // enough (point, chunk) threads to fill the GPU, at least 64 coefficients per chunk
+    u64 nchunks = ((u64)1 << 17) / n_points;
+    const u64 max_chunks = (n_coeffs + 63) / 64;
+    if (nchunks > max_chunks) nchunks = max_chunks;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > 65535) nchunks = 65535;
+    const u64 chunk_len = (n_coeffs + nchunks - 1) / nchunks;
+    nchunks = (n_coeffs + chunk_len - 1) / chunk_len;
+    u64 *partial = nullptr;
+    B2S_CUDA(cudaMallocAsync(&partial, sizeof(u64) * 3 * nchunks * n_points, st));
+    const dim3 grid(blocks, (unsigned)nchunks);
+#define EV(CP, PP)                                                                                                      \
+    eval_chunk_kernel<CP, PP><<<grid, 128, 0, st>>>(d_coeffs, coeff_stride, n_coeffs, d_points, point_stride, n_points, \
+                                                    chunk_len, partial)
     if (coeff_planes == 1 && point_planes == 1)
         EV(1, 1);
     else if (coeff_planes == 3 && point_planes == 1)
         EV(3, 1);
     else if (coeff_planes == 1 && point_planes == 3)
         EV(1, 3);
-    else if (coeff_planes == 3 && point_planes == 3)
+    else
         EV(3, 3);
-    else {
-        b2s_set_error("eval_points: planes must be 1 or 3");
-        return B2S_ERR_ARG;
-    }
 #undef EV
     B2S_LAUNCHED();
+    eval_sum_kernel<<<blocks, 128, 0, st>>>(partial, n_points, (u32)nchunks, out_planes, d_out, out_stride);
+    B2S_LAUNCHED();
+    cudaFreeAsync(partial, st);
     return 0;
 }
 
