@@ -125,6 +125,10 @@ int b2s_merkle_field(const uint64_t *d_planes, uint64_t plane_stride, uint64_t n
  * (code/merkle.py:26).  d_nodes holds 2*npo2 slots. */
 int b2s_merkle_blobs(const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_leafs, uint64_t npo2,
                      uint8_t *d_nodes, void *stream);
+/* code/merkle.py:35-41 alone: the inner nodes above `npo2` digests that the caller has placed in
+ * slots [npo2, 2*npo2) of d_nodes (multi-GPU trees: the top levels over the subtree roots that the
+ * ranks exchanged). */
+int b2s_merkle_upper(uint8_t *d_nodes, uint64_t npo2, void *stream);
 /* code/merkle.py:46-52 open(): copies the `depth` sibling digests of each index, leaf
  * level first, to host memory: h_paths[q*depth*64 ...].  Synchronises. */
 int b2s_merkle_open(const uint8_t *d_nodes, uint64_t npo2, const uint64_t *h_indices, uint32_t n_indices,

@@ -487,6 +487,9 @@ static void merkle_upper(u8 *nodes, u64 npo2) {
         orc_blake2b(nodes + 128 * k, 128, nodes + 64 * k);
 }
 
+/* code/merkle.py:35-41 for callers that already hold the leaf-level digests in slots [npo2, 2 npo2) */
+void orc_merkle_upper(u8 *nodes, u64 npo2) { merkle_upper(nodes, npo2); }
+
 int orc_merkle_field(const orc_leaf_templates *tp, const u64 *planes, u64 stride, u64 n, u8 *nodes) {
     if (n == 0 || (n & (n - 1))) return -1;
     memset(nodes, 0, 64);

@@ -74,6 +74,8 @@ def lib():
         L.orc_quotients.argtypes = [vp, u64, C.c_uint32, u64, C.c_uint32, vp, vp, vp, C.c_uint32, C.c_uint32, u64, u64,
                                     u64, u64, vp]
         L.orc_quotients.restype = C.c_int
+        L.orc_merkle_upper.argtypes = [vp, u64]
+        L.orc_merkle_upper.restype = None
         L.orc_blake2b.restype = None
         L.orc_blake2b.argtypes = [C.c_char_p, u64, vp]
         L.orc_pickle_uint.restype = C.c_uint32
@@ -217,6 +219,13 @@ def fri_fold(cw, alpha, offset, omega):
     out = np.empty((3, n // 2), dtype=np.uint64)
     lib().orc_fri_fold(_p(cw), n, n, _x3(alpha), offset, omega, _p(out), n // 2)
     return out
+
+
+def merkle_upper(nodes):
+    """(2 npo2, 64) uint8 with the digests of level npo2 filled in -> all inner nodes, in place"""
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint8)
+    lib().orc_merkle_upper(_p(nodes), nodes.shape[0] // 2)
+    return nodes
 
 
 def quotients(cw, shift, mono_off, coeffs, factors, kind, height, omicron_inv, offset, omega):

@@ -375,6 +375,14 @@ extern "C" int b2s_merkle_field(const uint64_t *d_planes, uint64_t plane_stride,
     return merkle_field_run(d_planes, plane_stride, n, tpl, d_nodes, (cudaStream_t)stream);
 }
 
+extern "C" int b2s_merkle_upper(uint8_t *d_nodes, uint64_t npo2, void *stream) {
+    if (npo2 == 0 || (npo2 & (npo2 - 1))) {
+        b2s_set_error("merkle_upper: node count must be a power of two, got %llu", (unsigned long long)npo2);
+        return B2S_ERR_ARG;
+    }
+    return merkle_upper_run(d_nodes, npo2, (cudaStream_t)stream);
+}
+
 extern "C" int b2s_merkle_blobs(const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_leafs, uint64_t npo2,
                                 uint8_t *d_nodes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;

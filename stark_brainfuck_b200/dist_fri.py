@@ -1,0 +1,291 @@
+"""Multi-GPU FRI prover: ONE codeword sharded over the ranks (FRI row).
+
+code/fri.py:178-199 (prove = commit + query) with the round-0 codeword spread over G = 2^g ranks
+of a torch.distributed group (NCCL on GPUs, gloo in the CPU tests).  The transcript every rank
+produces is byte-identical to the one a single device (and the reference) produces.
+
+Layout.  Split-and-fold pairs element i with i + N/2 (code/fri.py:127), so rank r holds the PAIR
+of blocks  A_r = c[r*B, (r+1)*B)  and  B_r = c[N/2 + r*B, N/2 + (r+1)*B),  B = N/(2G):
+
+  round 0   no exchange: rank r folds [A_r | B_r] locally (the fold kernel sees a length-2B
+            codeword on the coset offset*omega^(r*B); (omega^(N/2) = -1 makes that exact) and
+            gets block r of the next codeword plus the Merkle subtree over it;
+  round k   while more than one rank is active: the upper half of the active ranks send their
+            block to rank - active/2 (one point-to-point message of B elements), the lower half
+            fold [own | received]; active halves.  After log2 G rounds rank 0 owns the (small)
+            rest and finishes like the single-device prover.
+  trees     every block is a subtree of the round's Merkle tree; the ranks all-gather the
+            subtree roots (64 B each) and each computes the few top levels itself
+            (b2s_merkle_upper), so every rank knows every round's root and can run Fiat-Shamir
+            (code/fri.py:120) without a broadcast.
+  queries   opened leaves and authentication paths are collected with one all-reduce per query
+            round (owners contribute, everybody else zeros); the top levels come from the
+            replicated top tree.
+
+All ranks execute the same sequence of collectives (SPMD) and end with identical proof streams.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .glue import DeviceCodeword, NodeView
+
+P = 18446744069414584321
+
+
+def scatter_pair_blocks(planes, rank, world):
+    """host helper: the (A_r, B_r) blocks rank `rank` owns of a full codeword given as (3, N) planes"""
+    a = np.asarray(planes, dtype=np.uint64)
+    n = a.shape[1]
+    blk = n // (2 * world)
+    lo = rank * blk
+    return (np.ascontiguousarray(a[:, lo:lo + blk]), np.ascontiguousarray(a[:, n // 2 + lo:n // 2 + lo + blk]))
+
+
+class _Layout:
+    """where the leaves of one round live: subtree s covers leaves [s*blk, (s+1)*blk) and is slot
+    `slot(s)` of rank `rank(s)`"""
+
+    def __init__(self, n, blk, world, paired):
+        self.n, self.blk, self.world, self.paired = n, blk, world, paired
+        self.subtrees = n // blk
+
+    def owner(self, s):
+        if self.paired:  # round 0: subtrees 0..G-1 are the A blocks, G..2G-1 the B blocks
+            return s % self.world, s // self.world
+        return s, 0
+
+
+class DistCodeword(DeviceCodeword):
+    """glue.DeviceCodeword over a codeword whose blocks live on several ranks; prefetch() is a
+    collective (every rank must call it with the same indices, which SPMD Fiat-Shamir ensures)"""
+
+    def __init__(self, df, layout, local_planes, xfield):
+        self._glue = df.glue
+        self._df = df
+        self._layout = layout
+        self._local = local_planes  # slot -> (3, blk) device tensor (None on ranks that own nothing)
+        self._xfield = xfield
+        self._n = layout.n
+        self._cache = {}
+
+    def prefetch(self, indices):
+        need = [i for i in dict.fromkeys(indices) if i not in self._cache]
+        if not need:
+            return
+        for i in need:
+            if not 0 <= i < self._n:
+                raise IndexError("list index out of range")
+        lay, df = self._layout, self._df
+        vals = np.zeros((len(need), 3), dtype=np.uint64)
+        mine = {}
+        for pos, i in enumerate(need):
+            r, slot = lay.owner(i // lay.blk)
+            if r == df.rank:
+                mine.setdefault(slot, []).append((pos, i % lay.blk))
+        for slot, items in mine.items():
+            got = df.eng.gather(self._local[slot], [j for _, j in items])
+            vals[[pos for pos, _ in items]] = got
+        vals = df.sum_over_ranks(vals.view(np.int64)).view(np.uint64)
+        mk, xf = self._glue.B.make_xfe, self._xfield
+        for i, v in zip(need, vals.tolist()):
+            self._cache[i] = mk(v[0], v[1], v[2], xf)
+
+    def materialize(self):
+        self.prefetch(range(self._n))
+        return [self._cache[i] for i in range(self._n)]
+
+
+class DistNodeView(NodeView):
+    """glue.NodeView over a tree whose bottom levels are per-rank subtrees and whose top levels
+    (above the subtree roots) are replicated on every rank"""
+
+    def __init__(self, df, layout, local_nodes, top):
+        self._df = df
+        self._layout = layout
+        self._local = local_nodes  # slot -> (2 blk, 64) uint8 heap of the local subtree
+        self._npo2 = self._n = layout.n
+        self._cache = dict(top)    # heap index -> bytes for every node of index < 2 * subtrees
+
+    def _fetch_all(self):
+        raise NotImplementedError("a sharded tree is only opened, never listed")
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            self._fetch_all()
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError("list index out of range")
+        v = self._cache.get(k)
+        if v is None:
+            if k == 0:
+                from hashlib import blake2b
+                v = self._cache[0] = blake2b(self._ZERO32 + self[1]).digest()
+            else:
+                raise KeyError("node %d of a sharded tree was not prefetched (prefetch_paths is collective)" % k)
+        return v
+
+    def prefetch_paths(self, indices, depth):
+        lay, df = self._layout, self._df
+        low = lay.blk.bit_length() - 1  # levels inside a subtree
+        if low == 0:
+            return
+        n = lay.n
+        need = [i for i in dict.fromkeys(indices) if 0 <= i < n
+                and any(((n | i) >> j) ^ 1 not in self._cache for j in range(low))]
+        if not need:
+            return
+        buf = np.zeros((len(need), low, 64), dtype=np.uint8)
+        mine = {}
+        for pos, i in enumerate(need):
+            r, slot = lay.owner(i // lay.blk)
+            if r == df.rank:
+                mine.setdefault(slot, []).append((pos, i % lay.blk))
+        for slot, items in mine.items():
+            paths = df.eng.merkle_open(self._local[slot], [j for _, j in items])
+            for (pos, _), path in zip(items, paths):
+                buf[pos] = np.frombuffer(b"".join(path), dtype=np.uint8).reshape(low, 64)
+        buf = df.sum_over_ranks(buf)
+        for pos, i in enumerate(need):
+            k = n | i
+            for j in range(low):
+                sib = (k >> j) ^ 1
+                if sib not in self._cache:
+                    self._cache[sib] = buf[pos, j].tobytes()
+
+
+class DistFri:
+    def __init__(self, glue, group=None):
+        self.glue = glue
+        self.eng = glue.engine
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        assert self.world & (self.world - 1) == 0, "power-of-two number of ranks"
+        self.exchanged_bytes = 0  # payload this rank sent or received point to point (for reports)
+
+    # ---- collectives -----------------------------------------------------------------------
+    def sum_over_ranks(self, arr):
+        """numpy array, non-zero on exactly one rank per entry -> the same array on every rank"""
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.eng.device)
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def _gather_roots(self, mine, per_rank):
+        """all-gather of `per_rank` 64-byte digests per rank -> (world, per_rank, 64) uint8 on the device"""
+        out = torch.empty(self.world * per_rank * 64, dtype=torch.uint8, device=self.eng.device)
+        dist.all_gather_into_tensor(out, mine.contiguous().view(-1), group=self.group)
+        return out.view(self.world, per_rank, 64)
+
+    def _tree(self, Merkle, layout, local_planes, local_nodes, xfield):
+        """Merkle object of one round: subtree roots exchanged, top levels computed on every rank"""
+        eng = self.eng
+        slots = 2 if layout.paired else 1
+        mine = torch.zeros((slots, 64), dtype=torch.uint8, device=eng.device)
+        for s in range(slots):
+            if local_nodes[s] is not None:
+                mine[s] = local_nodes[s][1]
+        roots = self._gather_roots(mine, slots)  # [rank][slot]
+        S = layout.subtrees
+        heap = torch.zeros((2 * S, 64), dtype=torch.uint8, device=eng.device)
+        if layout.paired:
+            heap[S:] = roots.transpose(0, 1).reshape(S, 64)  # subtree s = slot s // G of rank s % G
+        else:
+            heap[S:] = roots[:S, 0]
+        if S > 1:
+            eng.merkle_upper(heap)
+        raw = eng.download_bytes(heap)
+        top = {k: raw[64 * k:64 * k + 64] for k in range(1, 2 * S)}
+        tree = Merkle.__new__(Merkle)
+        tree.num_leafs = layout.n
+        tree.depth = layout.n.bit_length() - 1
+        tree.leafs = DistCodeword(self, layout, local_planes, xfield)
+        tree.nodes = DistNodeView(self, layout, local_nodes, top)
+        return tree
+
+    def _exchange(self, blk_planes, active):
+        """upper half of the active ranks -> lower half; returns [own | received] on the receivers"""
+        half = active // 2
+        r = self.rank
+        if r >= active:
+            return None
+        nbytes = blk_planes.numel() * 8
+        self.exchanged_bytes += nbytes
+        if r >= half:
+            dist.send(blk_planes.contiguous(), group=self.group, group_dst=r - half)
+            return None
+        other = torch.empty_like(blk_planes)
+        dist.recv(other, group=self.group, group_src=r + half)
+        return torch.cat([blk_planes, other], dim=1)
+
+    # ---- code/fri.py:91-139 + :178-199 -------------------------------------------------------
+    def prove(self, fri, block_a, block_b, proof_stream, Merkle):
+        """block_a / block_b: this rank's (3, B) device planes of the round-0 codeword (see module
+        docstring; scatter_pair_blocks() cuts them from a full codeword).  Pushes exactly what
+        Fri.prove pushes and returns its top_level_indices -- on every rank."""
+        glue, eng, G, rank = self.glue, self.eng, self.world, self.rank
+        xfield = fri.field
+        N = fri.domain.length
+        blk = N // (2 * G)
+        assert blk >= 1 and blk * 2 * G == N and block_a.shape == (3, blk) and block_b.shape == (3, blk), \
+            "initial codeword length does not match length of initial codeword"
+        num_rounds = fri.num_rounds()
+        omega = glue.base_value(fri.domain.omega)
+        offset = glue.base_value(fri.domain.offset)
+        tpl = glue.xfe_templates(xfield)
+
+        layout = _Layout(N, blk, G, paired=True)
+        planes = [block_a, block_b]
+        nodes = [eng.merkle_field(block_a, tpl), eng.merkle_field(block_b, tpl)]
+        active = G
+        trees, codewords = [], []
+        for r in range(num_rounds):
+            n = layout.n
+            assert pow(omega, n - 1, P) == pow(omega, P - 2, P), "error in commit: omega does not have the right order!"
+            tree = self._tree(Merkle, layout, planes, nodes, xfield)
+            root = tree.root()
+            if r > 0:
+                proof_stream.push(root)
+            if r == num_rounds - 1:
+                break
+            alpha = xfield.sample(proof_stream.prover_fiat_shamir())
+            codewords.append(tree.leafs)
+            trees.append(tree)
+            a = [c.value for c in alpha.polynomial.coefficients]
+            a += [0] * (3 - len(a))
+            # the pair buffer [first half block | second half block] this rank folds, if any
+            if layout.paired:
+                pair = torch.cat([planes[0], planes[1]], dim=1)
+                nxt_layout = _Layout(n // 2, blk, G, paired=False)
+            elif active > 1:
+                pair = self._exchange(planes[0], active)
+                active //= 2
+                nxt_layout = _Layout(n // 2, layout.blk, G, paired=False)
+            else:
+                pair = planes[0] if rank == 0 else None
+                nxt_layout = _Layout(n // 2, layout.blk // 2, G, paired=False)
+            if pair is not None:
+                # rank `rank` folds the sub-coset that starts at omega^(rank * block)
+                off_local = offset * pow(omega, rank * (pair.shape[1] // 2), P) % P
+                nxt, nn = eng.fri_fold(pair, a, off_local, omega, tpl)
+                planes, nodes = [nxt], [nn]
+            else:
+                planes, nodes = [None], [None]
+            layout = nxt_layout
+            omega = omega * omega % P
+            offset = offset * offset % P
+        last = tree.leafs.materialize()
+        proof_stream.push(last)
+        codewords.append(last)
+
+        # code/fri.py:186-199
+        top_level_indices = fri.sample_indices(proof_stream.prover_fiat_shamir(), len(codewords[1]),
+                                               len(codewords[-1]), fri.num_colinearity_tests)
+        indices = [i for i in top_level_indices]
+        for i in range(len(trees) - 1):
+            indices = [index % (len(codewords[i]) // 2) for index in indices]
+            glue.fri_query(fri, trees[i], trees[i + 1], indices, proof_stream)
+        indices = [index % len(codewords[-1]) for index in indices]
+        glue.fri_query_last(fri, trees[-1], codewords[-1], indices, proof_stream)
+        return top_level_indices

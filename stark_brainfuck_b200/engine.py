@@ -144,6 +144,11 @@ class Engine:
         self.check(self.lib.b2s_merkle_blobs(_ptr(d_data), _ptr(d_offs), n, npo2, _ptr(nodes), self.stream_ptr()))
         return nodes
 
+    def merkle_upper(self, nodes):
+        """inner nodes above the digests in slots [npo2, 2 npo2) of `nodes` ((2 npo2, 64) uint8), in place"""
+        self.check(self.lib.b2s_merkle_upper(_ptr(nodes), nodes.shape[0] // 2, self.stream_ptr()))
+        return nodes
+
     def merkle_open(self, nodes, indices):
         """code/merkle.py:46-52 for several indices: list of lists of 64-byte digests"""
         npo2 = nodes.shape[0] // 2

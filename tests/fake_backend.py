@@ -114,6 +114,12 @@ class FakeLib:
         _u8(_addr(d_nodes), 128 * npo2)[:] = orc.merkle_blobs(blobs).reshape(-1)
         return 0
 
+    def b2s_merkle_upper(self, d_nodes, npo2, stream):
+        self.launches += 1
+        view = _u8(_addr(d_nodes), 128 * npo2).reshape(-1, 64)
+        view[:] = orc.merkle_upper(view.copy())
+        return 0
+
     def b2s_merkle_open(self, d_nodes, npo2, h_idx, n_idx, h_paths, stream):
         self.launches += 1
         nodes = _u8(_addr(d_nodes), 128 * npo2).reshape(-1, 64)

@@ -58,3 +58,58 @@ def test_shard_units():
             assert got == list(range(n))
             sizes = [len(shard_units(n, r, world)) for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _fri_worker(rank, world, port, logn, expansion, s, seed, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import frontend_cases as fc
+        from fake_backend import fake_engine
+        from stark_brainfuck_b200 import mirror
+        from stark_brainfuck_b200.dist_fri import DistFri, scatter_pair_blocks
+        from stark_brainfuck_b200.glue import Glue
+        mirror.register()
+        glue = Glue(mirror.binding, fake_engine())
+        mirror.set_glue(glue)
+        m = mirror
+        env = fc.make_env(m.algebra, m.univariate, m.extension_field, m.ntt, m.merkle, m.ip, m.fri)
+        n = 1 << logn
+        fri = env.Fri(env.field.generator(), env.field.primitive_nth_root(n), n, expansion, s, env.xfield)
+        _, planes = fc.fri_input(env, logn, expansion, seed)
+        a, b = scatter_pair_blocks(planes, rank, world)
+        df = DistFri(glue)
+        ps = env.ProofStream()
+        top = df.prove(fri, glue.engine.upload(a), glue.engine.upload(b), ps, env.Merkle)
+        ser = ps.serialize()
+        ok = None
+        if rank == 0 and logn <= 8:  # the (mirror of the) reference's verifier accepts the sharded proof
+            cw = [fc.X(env, *[int(planes[j][i]) for j in range(3)]) for i in range(n)]
+            ok = fri.verify(env.ProofStream().deserialize(ser), env.Merkle(cw).root())
+        ret[rank] = (top, len(ps.objects), [o.hex() for o in ps.objects if isinstance(o, bytes)], ser, ok,
+                     df.exchanged_bytes)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,logn", [(2, 6), (2, 8), (4, 8), (2, 10), (4, 10), (8, 10)])
+def test_sharded_fri_transcript_matches_golden(world, logn):
+    """one codeword over `world` ranks: every rank's transcript is the reference's, byte for byte"""
+    import hashlib
+    from util import golden
+    e = golden("fri_small.json")["gv6"][str(logn)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() + logn * 11 + world) % 2000
+    mp.spawn(_fri_worker, args=(world, port, logn, 4, 8, 200 + logn, ret), nprocs=world, join=True)
+    for r in range(world):
+        top, nobj, roots, ser, ok, _ = ret[r]
+        assert top == e["top_level_indices"] and nobj == e["num_objects"] and roots == e["round_roots"]
+        assert len(ser) == e["transcript_len"] and hashlib.sha256(ser).hexdigest() == e["transcript_sha256"]
+    if logn <= 8:
+        assert ret[0][4] is True
+    # the only bulk traffic is one block per active rank pair per round after the first
+    assert ret[0][5] > 0 and ret[0][5] <= 3 * 8 * (1 << logn) // (2 * world) * (world.bit_length() - 1)

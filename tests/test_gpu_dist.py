@@ -24,3 +24,17 @@ def test_sharded_ntt_two_gpus():
     assert rep["nccl"]["matches_oracle"] is True and rep["nccl"]["roundtrip_exact"] is True
     if "error" not in rep.get("p2p", {"error": 1}):
         assert rep["p2p"]["matches_oracle"] is True and rep["p2p"]["roundtrip_exact"] is True
+
+
+def test_sharded_fri_two_gpus():
+    """one FRI proof over 2 GPUs: transcripts byte-identical to the golden (reference) ones"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(HERE, "dist_fri_gpu_check.py"), "--logs", "8,10,16",
+           "--iters", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rep = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert all(c["transcripts_identical"] for c in rep["cases"].values())
