@@ -4,23 +4,27 @@ code/fri.py:178-199 (prove = commit + query) with the round-0 codeword spread ov
 of a torch.distributed group (NCCL on GPUs, gloo in the CPU tests).  The transcript every rank
 produces is byte-identical to the one a single device (and the reference) produces.
 
-Layout.  Split-and-fold pairs element i with i + N/2 (code/fri.py:127), so rank r holds the PAIR
-of blocks  A_r = c[r*B, (r+1)*B)  and  B_r = c[N/2 + r*B, N/2 + (r+1)*B),  B = N/(2G):
+Layout.  Split-and-fold pairs element i with i + n/2 (code/fri.py:127), so rank r starts with the
+PAIR of blocks  A_r = c[r*B, (r+1)*B)  and  B_r = c[N/2 + r*B, N/2 + (r+1)*B),  B = N/(2G):
 
-  round 0   no exchange: rank r folds [A_r | B_r] locally (the fold kernel sees a length-2B
-            codeword on the coset offset*omega^(r*B); (omega^(N/2) = -1 makes that exact) and
-            gets block r of the next codeword plus the Merkle subtree over it;
-  round k   while more than one rank is active: the upper half of the active ranks send their
-            block to rank - active/2 (one point-to-point message of B elements), the lower half
-            fold [own | received]; active halves.  After log2 G rounds rank 0 owns the (small)
-            rest and finishes like the single-device prover.
-  trees     every block is a subtree of the round's Merkle tree; the ranks all-gather the
-            subtree roots (64 B each) and each computes the few top levels itself
-            (b2s_merkle_upper), so every rank knows every round's root and can run Fiat-Shamir
-            (code/fri.py:120) without a broadcast.
-  queries   opened leaves and authentication paths are collected with one all-reduce per query
-            round (owners contribute, everybody else zeros); the top levels come from the
-            replicated top tree.
+  round 0    no exchange: rank r folds [A_r | B_r] locally (the fold kernel sees a length-2B
+             codeword on the coset offset*omega^(r*B); omega^(n/2) = -1 makes that exact) and
+             gets block r of the next codeword plus the Merkle subtree over it;
+  round k    balanced butterfly: the owners of blocks s and s + G/2 swap HALF a block each (the
+             lower owner keeps the lower halves, the upper owner the upper halves), both fold
+             their b/2 pairs, so every rank stays busy with 1/G of the round's work and the next
+             codeword again has G blocks (of half the size, owners permuted -- _Layout.owners);
+  replicate  once blocks are small (<= replicate_below elements) one all-gather gives every
+             rank the whole codeword and the remaining rounds run redundantly on every rank with
+             no further communication;
+  trees      every block is a subtree of the round's Merkle tree; the ranks all-gather the
+             subtree roots (64 B each) and each computes the few top levels itself
+             (b2s_merkle_upper), so every rank knows every round's root and can run Fiat-Shamir
+             (code/fri.py:120) without a broadcast;
+  queries    the indices of all rounds follow from the sampled top-level indices, so all opened
+             leaves and the in-subtree parts of all authentication paths are collected with ONE
+             all-reduce (owners contribute, everybody else zeros); the top levels come from the
+             replicated top trees.
 
 All ranks execute the same sequence of collectives (SPMD) and end with identical proof streams.
 """
@@ -44,16 +48,18 @@ def scatter_pair_blocks(planes, rank, world):
 
 class _Layout:
     """where the leaves of one round live: subtree s covers leaves [s*blk, (s+1)*blk) and is slot
-    `slot(s)` of rank `rank(s)`"""
+    `slot` of rank `rank`, (rank, slot) = owner(s)"""
 
-    def __init__(self, n, blk, world, paired):
-        self.n, self.blk, self.world, self.paired = n, blk, world, paired
+    def __init__(self, n, blk, world, owners=None):
+        self.n, self.blk, self.world = n, blk, world
         self.subtrees = n // blk
+        self.paired = owners is None  # round 0: subtrees 0..G-1 are the A blocks, G..2G-1 the B blocks
+        self.owners = owners          # later rounds: one block per rank, owners[s] = rank of subtree s
 
     def owner(self, s):
-        if self.paired:  # round 0: subtrees 0..G-1 are the A blocks, G..2G-1 the B blocks
+        if self.paired:
             return s % self.world, s // self.world
-        return s, 0
+        return self.owners[s], 0
 
 
 class DistCodeword(DeviceCodeword):
@@ -69,13 +75,17 @@ class DistCodeword(DeviceCodeword):
         self._n = layout.n
         self._cache = {}
 
-    def prefetch(self, indices):
+    # prefetch = wanted() -> local() -> [sum over ranks] -> fill(); DistFri.prefetch_queries runs the
+    # middle step ONCE for all trees and codewords of the query phase
+    def wanted(self, indices):
         need = [i for i in dict.fromkeys(indices) if i not in self._cache]
-        if not need:
-            return
         for i in need:
             if not 0 <= i < self._n:
                 raise IndexError("list index out of range")
+        return need
+
+    def local(self, need):
+        """(len(need), 3) uint64: the elements this rank owns, zeros elsewhere"""
         lay, df = self._layout, self._df
         vals = np.zeros((len(need), 3), dtype=np.uint64)
         mine = {}
@@ -84,12 +94,18 @@ class DistCodeword(DeviceCodeword):
             if r == df.rank:
                 mine.setdefault(slot, []).append((pos, i % lay.blk))
         for slot, items in mine.items():
-            got = df.eng.gather(self._local[slot], [j for _, j in items])
-            vals[[pos for pos, _ in items]] = got
-        vals = df.sum_over_ranks(vals.view(np.int64)).view(np.uint64)
+            vals[[pos for pos, _ in items]] = df.eng.gather(self._local[slot], [j for _, j in items])
+        return vals
+
+    def fill(self, need, vals):
         mk, xf = self._glue.B.make_xfe, self._xfield
         for i, v in zip(need, vals.tolist()):
             self._cache[i] = mk(v[0], v[1], v[2], xf)
+
+    def prefetch(self, indices):
+        need = self.wanted(indices)
+        if need:
+            self.fill(need, self._df.sum_over_ranks(self.local(need)))
 
     def materialize(self):
         self.prefetch(range(self._n))
@@ -126,16 +142,17 @@ class DistNodeView(NodeView):
                 raise KeyError("node %d of a sharded tree was not prefetched (prefetch_paths is collective)" % k)
         return v
 
-    def prefetch_paths(self, indices, depth):
-        lay, df = self._layout, self._df
+    def wanted(self, indices):
+        lay = self._layout
         low = lay.blk.bit_length() - 1  # levels inside a subtree
-        if low == 0:
-            return
         n = lay.n
-        need = [i for i in dict.fromkeys(indices) if 0 <= i < n
+        return [i for i in dict.fromkeys(indices) if 0 <= i < n
                 and any(((n | i) >> j) ^ 1 not in self._cache for j in range(low))]
-        if not need:
-            return
+
+    def local(self, need):
+        """(len(need), low, 64) uint8: the in-subtree part of the paths this rank owns, zeros elsewhere"""
+        lay, df = self._layout, self._df
+        low = lay.blk.bit_length() - 1
         buf = np.zeros((len(need), low, 64), dtype=np.uint8)
         mine = {}
         for pos, i in enumerate(need):
@@ -146,13 +163,21 @@ class DistNodeView(NodeView):
             paths = df.eng.merkle_open(self._local[slot], [j for _, j in items])
             for (pos, _), path in zip(items, paths):
                 buf[pos] = np.frombuffer(b"".join(path), dtype=np.uint8).reshape(low, 64)
-        buf = df.sum_over_ranks(buf)
+        return buf
+
+    def fill(self, need, buf):
+        n = self._layout.n
         for pos, i in enumerate(need):
             k = n | i
-            for j in range(low):
+            for j in range(buf.shape[1]):
                 sib = (k >> j) ^ 1
                 if sib not in self._cache:
                     self._cache[sib] = buf[pos, j].tobytes()
+
+    def prefetch_paths(self, indices, depth):
+        need = self.wanted(indices)
+        if need:
+            self.fill(need, self._df.sum_over_ranks(self.local(need)))
 
 
 class DistFri:
@@ -168,9 +193,27 @@ class DistFri:
     # ---- collectives -----------------------------------------------------------------------
     def sum_over_ranks(self, arr):
         """numpy array, non-zero on exactly one rank per entry -> the same array on every rank"""
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.eng.device)
+        if self.world == 1:
+            return arr
+        a = np.ascontiguousarray(arr)
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1)).to(self.eng.device)  # bytes: no carries to worry about
         dist.all_reduce(t, group=self.group)
-        return t.cpu().numpy()
+        return t.cpu().numpy().view(a.dtype).reshape(a.shape)
+
+    def prefetch_queries(self, requests):
+        """everything the query phase will open -- requests = [(DistCodeword | DistNodeView, indices)] --
+        with ONE all-reduce instead of one per tree and round"""
+        jobs = [(obj, obj.wanted(idx)) for obj, idx in requests]
+        jobs = [(obj, need) for obj, need in jobs if need]
+        if not jobs:
+            return
+        parts = [np.ascontiguousarray(obj.local(need)) for obj, need in jobs]
+        flat = np.concatenate([p.view(np.uint8).reshape(-1) for p in parts])
+        flat = self.sum_over_ranks(flat)
+        pos = 0
+        for (obj, need), p in zip(jobs, parts):
+            obj.fill(need, flat[pos:pos + p.nbytes].view(p.dtype).reshape(p.shape))
+            pos += p.nbytes
 
     def _gather_roots(self, mine, per_rank):
         """all-gather of `per_rank` 64-byte digests per rank -> (world, per_rank, 64) uint8 on the device"""
@@ -192,7 +235,7 @@ class DistFri:
         if layout.paired:
             heap[S:] = roots.transpose(0, 1).reshape(S, 64)  # subtree s = slot s // G of rank s % G
         else:
-            heap[S:] = roots[:S, 0]
+            heap[S:] = roots[layout.owners, 0]
         if S > 1:
             eng.merkle_upper(heap)
         raw = eng.download_bytes(heap)
@@ -204,23 +247,38 @@ class DistFri:
         tree.nodes = DistNodeView(self, layout, local_nodes, top)
         return tree
 
-    def _exchange(self, blk_planes, active):
-        """upper half of the active ranks -> lower half; returns [own | received] on the receivers"""
-        half = active // 2
-        r = self.rank
-        if r >= active:
-            return None
-        nbytes = blk_planes.numel() * 8
-        self.exchanged_bytes += nbytes
-        if r >= half:
-            dist.send(blk_planes.contiguous(), group=self.group, group_dst=r - half)
-            return None
-        other = torch.empty_like(blk_planes)
-        dist.recv(other, group=self.group, group_src=r + half)
-        return torch.cat([blk_planes, other], dim=1)
+    def _butterfly(self, own, layout):
+        """round k >= 1: swap half a block with the owner of the paired subtree; returns the
+        [low | high] pair buffer this rank folds, the index of the subtree it produces and the
+        owners of the next round's subtrees"""
+        S, b = layout.subtrees, layout.blk
+        s = layout.owners.index(self.rank)
+        h = b // 2
+        lower = s < S // 2
+        partner = layout.owners[s + S // 2] if lower else layout.owners[s - S // 2]
+        send = own[:, h:].contiguous() if lower else own[:, :h].contiguous()
+        recv = torch.empty_like(send)
+        ops = [dist.P2POp(dist.isend, send, group=self.group, group_peer=partner),
+               dist.P2POp(dist.irecv, recv, group=self.group, group_peer=partner)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        self.exchanged_bytes += send.numel() * 8
+        if lower:
+            pair, t = torch.cat([own[:, :h], recv], dim=1), 2 * s
+        else:
+            pair, t = torch.cat([recv, own[:, h:]], dim=1), 2 * (s - S // 2) + 1
+        owners = [layout.owners[(u >> 1) + (u & 1) * (S // 2)] for u in range(S)]
+        return pair, t, owners
+
+    def _replicate(self, own, layout):
+        """all-gather of the blocks: the whole codeword of this round on every rank"""
+        b = layout.blk
+        out = torch.empty(self.world * 3 * b, dtype=own.dtype, device=own.device)
+        dist.all_gather_into_tensor(out, own.contiguous().view(-1), group=self.group)
+        return out.view(self.world, 3, b)[layout.owners].permute(1, 0, 2).reshape(3, layout.n).contiguous()
 
     # ---- code/fri.py:91-139 + :178-199 -------------------------------------------------------
-    def prove(self, fri, block_a, block_b, proof_stream, Merkle):
+    def prove(self, fri, block_a, block_b, proof_stream, Merkle, replicate_below=1 << 12):
         """block_a / block_b: this rank's (3, B) device planes of the round-0 codeword (see module
         docstring; scatter_pair_blocks() cuts them from a full codeword).  Pushes exactly what
         Fri.prove pushes and returns its top_level_indices -- on every rank."""
@@ -235,15 +293,19 @@ class DistFri:
         offset = glue.base_value(fri.domain.offset)
         tpl = glue.xfe_templates(xfield)
 
-        layout = _Layout(N, blk, G, paired=True)
+        layout = _Layout(N, blk, G)  # None once the codeword is replicated
         planes = [block_a, block_b]
         nodes = [eng.merkle_field(block_a, tpl), eng.merkle_field(block_b, tpl)]
-        active = G
+        n = N
         trees, codewords = [], []
         for r in range(num_rounds):
-            n = layout.n
             assert pow(omega, n - 1, P) == pow(omega, P - 2, P), "error in commit: omega does not have the right order!"
-            tree = self._tree(Merkle, layout, planes, nodes, xfield)
+            if layout is not None:
+                tree = self._tree(Merkle, layout, planes, nodes, xfield)
+            else:
+                tree = Merkle.__new__(Merkle)
+                cache = DeviceCodeword(glue, planes[0], xfield)
+                glue.merkle_build(tree, cache, device_planes=planes[0], device_nodes=nodes[0], leaf_cache=cache)
             root = tree.root()
             if r > 0:
                 proof_stream.push(root)
@@ -254,25 +316,21 @@ class DistFri:
             trees.append(tree)
             a = [c.value for c in alpha.polynomial.coefficients]
             a += [0] * (3 - len(a))
-            # the pair buffer [first half block | second half block] this rank folds, if any
-            if layout.paired:
-                pair = torch.cat([planes[0], planes[1]], dim=1)
-                nxt_layout = _Layout(n // 2, blk, G, paired=False)
-            elif active > 1:
-                pair = self._exchange(planes[0], active)
-                active //= 2
-                nxt_layout = _Layout(n // 2, layout.blk, G, paired=False)
+            # the [low | high] pair buffer this rank folds and where its first pair sits in the round
+            if layout is None:
+                pair, first, layout_next = planes[0], 0, None
+            elif layout.paired:
+                pair, first = torch.cat([planes[0], planes[1]], dim=1), rank * blk
+                layout_next = _Layout(n // 2, blk, G, owners=list(range(G)))
+            elif G > 1 and layout.blk >= 2 and layout.blk > replicate_below:
+                pair, t, owners = self._butterfly(planes[0], layout)
+                first = t * (layout.blk // 2)
+                layout_next = _Layout(n // 2, layout.blk // 2, G, owners=owners)
             else:
-                pair = planes[0] if rank == 0 else None
-                nxt_layout = _Layout(n // 2, layout.blk // 2, G, paired=False)
-            if pair is not None:
-                # rank `rank` folds the sub-coset that starts at omega^(rank * block)
-                off_local = offset * pow(omega, rank * (pair.shape[1] // 2), P) % P
-                nxt, nn = eng.fri_fold(pair, a, off_local, omega, tpl)
-                planes, nodes = [nxt], [nn]
-            else:
-                planes, nodes = [None], [None]
-            layout = nxt_layout
+                pair, first, layout_next = self._replicate(planes[0], layout), 0, None
+            nxt, nn = eng.fri_fold(pair, a, offset * pow(omega, first, P) % P, omega, tpl)
+            planes, nodes, layout = [nxt], [nn], layout_next
+            n //= 2
             omega = omega * omega % P
             offset = offset * offset % P
         last = tree.leafs.materialize()
@@ -282,6 +340,18 @@ class DistFri:
         # code/fri.py:186-199
         top_level_indices = fri.sample_indices(proof_stream.prover_fiat_shamir(), len(codewords[1]),
                                                len(codewords[-1]), fri.num_colinearity_tests)
+        # the indices of every round follow from the top-level ones: fetch all remote openings at once
+        sq = fri.num_colinearity_tests
+        wanted, idx = {}, [i for i in top_level_indices]
+        for i in range(len(trees)):
+            half = len(codewords[i]) // 2
+            idx = [index % half for index in idx]
+            wanted.setdefault(i, []).extend(idx[:sq] + [j + half for j in idx[:sq]])
+            if i + 1 < len(trees):
+                wanted.setdefault(i + 1, []).extend(idx[:sq])
+        sharded = [i for i in wanted if isinstance(trees[i].nodes, DistNodeView)]
+        self.prefetch_queries([(trees[i].leafs, wanted[i]) for i in sharded] +
+                              [(trees[i].nodes, wanted[i]) for i in sharded])
         indices = [i for i in top_level_indices]
         for i in range(len(trees) - 1):
             indices = [index % (len(codewords[i]) // 2) for index in indices]

@@ -1,6 +1,6 @@
 """Multi-GPU parity + timing of the sharded FRI prover (stark_brainfuck_b200/dist_fri.py).  Launch:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29512 tests/dist_fri_gpu_check.py [--logs 10,16,20] [--big 24]
+        --master-port 29512 tests/dist_fri_gpu_check.py [--sizes 10,16,20] [--big 24]
 Every rank checks its transcript against the golden one (generated from the reference); for --big
 sizes (no golden) against the transcript of the same prover on a one-rank group.  Rank 0 prints one
 JSON line with wall-clock times (device-synchronised, max over ranks) of the sharded and the
@@ -23,7 +23,7 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--logs", default="10,16")
+    ap.add_argument("--sizes", default="10,16")
     ap.add_argument("--big", default="")
     ap.add_argument("--iters", type=int, default=3)
     args = ap.parse_args()
@@ -64,7 +64,7 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         return top, ps, float(dt.item()) * 1e3
 
-    for kind, logs in (("golden", args.logs), ("big", args.big)):
+    for kind, logs in (("golden", args.sizes), ("big", args.big)):
         for logn in [int(v) for v in logs.split(",") if v]:
             n = 1 << logn
             coeffs = rand_xfe(200 + logn, n // expansion) if kind == "golden" else \

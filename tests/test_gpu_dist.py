@@ -32,7 +32,7 @@ def test_sharded_fri_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29534", os.path.join(HERE, "dist_fri_gpu_check.py"), "--logs", "8,10,16",
+           "127.0.0.1", "--master-port", "29534", os.path.join(HERE, "dist_fri_gpu_check.py"), "--sizes", "8,10,16",
            "--iters", "1"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
