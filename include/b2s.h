@@ -176,6 +176,21 @@ int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, uint64_t shi
                   uint32_t zerofier_kind, uint64_t height, uint64_t omicron_inv, uint64_t offset, uint64_t omega,
                   uint64_t *d_out, int *h_zero_flag, void *stream);
 
+/* ---- nonlinear combination codeword --------------------------------
+ * code/brainfuck_stark.py:241-298: the reference builds, for every base / extension / quotient
+ * codeword c, the terms c and x^shift * c, and sums weight * term over all of them element by
+ * element.  Here
+ *     out[j] = sum_c (wa_c + wb_c * x_j^shift_c) * col_c[j],   x_j = offset * omega^j,  j < N.
+ * Column c is a base-field plane (h_planes[c] == 1; lifted like ExtensionField.lift,
+ * code/extension_field.py:113-116) or an extension-field plane triple (h_planes[c] == 3, planes
+ * h_strides[c] elements apart) anywhere in device memory: h_cols[c] is its DEVICE address; all
+ * h_* arrays live in HOST memory.  h_wa / h_wb: 3 coefficients per column; a column whose wb is
+ * zero has no shifted term (the randomizer codeword, :242).  d_out: 3 planes, out_stride apart.
+ * Synchronises. */
+int b2s_combination(const uint64_t *const *h_cols, const uint64_t *h_strides, const uint32_t *h_planes,
+                    const uint64_t *h_wa, const uint64_t *h_wb, const uint64_t *h_shifts, uint32_t n_cols, uint64_t N,
+                    uint64_t offset, uint64_t omega, uint64_t *d_out, uint64_t out_stride, void *stream);
+
 /* ---- multi-GPU exchange step of the four-step NTT (no counterpart in the single-process
  * reference) ------------------------------------------------------------
  * n = n1*n2, j = j1 + n1*j2.  The caller owns `rows` = n1/G columns j1 (first one: row_base) as

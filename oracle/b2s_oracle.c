@@ -366,6 +366,42 @@ int orc_quotients(const u64 *cw, u64 N, u32 width, u64 shift, u32 n_constraints,
     return flag;
 }
 
+/* code/brainfuck_stark.py:241-298, the nonlinear combination: terms c and x^shift * c of every
+ * codeword (:247-291; lift of base-field values, code/extension_field.py:113-116), weighted sum
+ * (:298).  out[j] = sum_c wa_c * col_c[j] + wb_c * (x_j^shift_c * col_c[j]), x_j = offset*omega^j.
+ * cols[c]: `planes[c]` (1 or 3) planes of N values, strides[c] apart; a zero wb means the column
+ * has no shifted term (the randomizer codeword, :242). */
+void orc_combination(const u64 *const *cols, const u64 *strides, const u32 *planes, const u64 *wa, const u64 *wb,
+                     const u64 *shifts, u32 n_cols, u64 N, u64 offset, u64 omega, u64 *out, u64 out_stride) {
+    u64 wi = 1;
+    for (u64 j = 0; j < N; ++j) {
+        const u64 x = orc_mul(offset, wi);
+        u64 acc[3] = {0, 0, 0}, t[3], u[3];
+        for (u32 c = 0; c < n_cols; ++c) {
+            u64 v[3] = {cols[c][j], 0, 0};
+            if (planes[c] == 3) {
+                v[1] = cols[c][strides[c] + j];
+                v[2] = cols[c][2 * strides[c] + j];
+            }
+            orc_xmul(wa + 3 * c, v, t); /* weight * unshifted term */
+            orc_xadd(acc, t, u);
+            memcpy(acc, u, sizeof(u));
+            if (wb[3 * c] | wb[3 * c + 1] | wb[3 * c + 2]) {
+                const u64 xs[3] = {orc_pow(x, shifts[c]), 0, 0};
+                u64 sv[3];
+                orc_xmul(xs, v, sv); /* lift(x^shift) * c[j] */
+                orc_xmul(wb + 3 * c, sv, t);
+                orc_xadd(acc, t, u);
+                memcpy(acc, u, sizeof(u));
+            }
+        }
+        out[j] = acc[0];
+        out[out_stride + j] = acc[1];
+        out[2 * out_stride + j] = acc[2];
+        wi = orc_mul(wi, omega);
+    }
+}
+
 /* ---------------------------------------------------------------- BLAKE2b-512 (RFC 7693) */
 static const u64 B2B_IV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL,
                               0xa54ff53a5f1d36f1ULL, 0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL,

@@ -75,6 +75,8 @@ def lib():
                                     u64, u64, vp]
         L.orc_quotients.restype = C.c_int
         L.orc_merkle_upper.argtypes = [vp, u64]
+        L.orc_combination.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, u64, u64, u64, vp, u64]
+        L.orc_combination.restype = None
         L.orc_merkle_upper.restype = None
         L.orc_blake2b.restype = None
         L.orc_blake2b.argtypes = [C.c_char_p, u64, vp]
@@ -218,6 +220,21 @@ def fri_fold(cw, alpha, offset, omega):
     n = cw.shape[1]
     out = np.empty((3, n // 2), dtype=np.uint64)
     lib().orc_fri_fold(_p(cw), n, n, _x3(alpha), offset, omega, _p(out), n // 2)
+    return out
+
+
+def combination(columns, wa, wb, shifts, offset, omega):
+    """nonlinear combination codeword; columns: list of (1, N) or (3, N) uint64 arrays -> (3, N)"""
+    cols = [np.ascontiguousarray(c, dtype=np.uint64).reshape(-1, np.shape(c)[-1]) for c in columns]
+    n, N = len(cols), cols[0].shape[1]
+    ptrs = (C.c_void_p * n)(*[c.ctypes.data for c in cols])
+    strides = np.full(n, N, dtype=np.uint64)
+    planes = np.array([c.shape[0] for c in cols], dtype=np.uint32)
+    wa = np.ascontiguousarray(wa, dtype=np.uint64).reshape(n, 3)
+    wb = np.ascontiguousarray(wb, dtype=np.uint64).reshape(n, 3)
+    shifts = np.ascontiguousarray(shifts, dtype=np.uint64).reshape(n)
+    out = np.empty((3, N), dtype=np.uint64)
+    lib().orc_combination(ptrs, _p(strides), _p(planes), _p(wa), _p(wb), _p(shifts), n, N, offset, omega, _p(out), N)
     return out
 
 

@@ -11,11 +11,20 @@ time lives in every importing module's globals.  install() therefore
   3. patches class attributes, which every importer shares: Polynomial.scale/evaluate_domain,
      Fri.Domain.evaluate/xevaluate/interpolate/xinterpolate, Fri.commit/query/query_last/prove,
      Merkle.__init__/open  (Merkle.root/verify and Fri.verify stay the reference's).
+  4. next rows: Table.*_quotients / PermutationArgument.quotient, SaltedMerkle.__init__, and the
+     nonlinear combination.  The combination is INLINE in BrainfuckStark.prove
+     (code/brainfuck_stark.py:241-298), so there is no attribute to rebind: prove() is recompiled
+     at install time from the reference's own source with that one block guarded by a call into
+     the glue (the block itself stays as the fallback) -- the in-memory equivalent of the hunk
+     shown in INTEGRATION.md.
 uninstall() restores every original (needed to time the CPU reference in the same process).
 """
 import importlib
+import inspect
 import os
 import sys
+import textwrap
+import warnings
 
 from .glue import Glue
 from .marshal import Binding
@@ -33,10 +42,35 @@ def current_glue():
     return _state["glue"] if _state else None
 
 
-def install(reference_dir=None, engine=None, quotients=True, salted=True):
+_COMB_BEGIN = "# compute terms of nonlinear combination polynomial"
+_COMB_END = "# commit to combination codeword"
+_COMB_HOOK = "__b2s_combination__"
+
+
+def guarded_prove_source(prove):
+    """Source of BrainfuckStark.prove with its nonlinear-combination block (between the two marker
+    comments, code/brainfuck_stark.py:241-298) kept as the fallback of a call to the hook.  Raises
+    LookupError when the markers are not where this reference version has them."""
+    src = textwrap.dedent(inspect.getsource(prove))
+    a, b = src.find(_COMB_BEGIN), src.find(_COMB_END)
+    if a < 0 or b < a or src.find(_COMB_BEGIN, a + 1) >= 0:
+        raise LookupError("nonlinear-combination block of BrainfuckStark.prove not found")
+    a, b = src.rindex("\n", 0, a) + 1, src.rindex("\n", 0, b) + 1
+    block = src[a:b]
+    if "combination_codeword = reduce(" not in block:
+        raise LookupError("nonlinear-combination block of BrainfuckStark.prove has an unexpected shape")
+    pad = block[:len(block) - len(block.lstrip())]
+    call = (pad + "combination_codeword = " + _COMB_HOOK + "(self.fri.domain, self.xfield, self.max_degree, "
+            "randomizer_codeword, base_codewords, base_degree_bounds, extension_codewords, extension_degree_bounds, "
+            "quotient_codewords, quotient_degree_bounds, weights)\n" + pad + "if combination_codeword is None:\n")
+    return src[:a] + call + textwrap.indent(block, "    ") + src[b:]
+
+
+def install(reference_dir=None, engine=None, quotients=True, salted=True, combination=True):
     """Patch the reference modules importable from `reference_dir` (or already on sys.path).
     `quotients=True` also moves the quotient-codeword loops of table.py / permutation_argument.py
-    (93 % of prove()) to the device, `salted=True` the trees of salted_merkle.py.
+    (93 % of prove()) to the device, `salted=True` the trees of salted_merkle.py,
+    `combination=True` the nonlinear combination inside BrainfuckStark.prove (see module docstring).
     Returns the Glue in use."""
     global _state
     if _state is not None:
@@ -114,6 +148,29 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True):
         set_attr(sm.SaltedMerkle, "__init__",
                  lambda self, data_array: glue.salted_merkle_build(self, data_array, lambda k: sm.urandom(k)))
 
+    # -- 6. next row: the nonlinear combination inside BrainfuckStark.prove -------
+    if combination:
+        try:
+            bs = importlib.import_module("brainfuck_stark")
+            prove = bs.BrainfuckStark.prove
+            code = compile(guarded_prove_source(prove), prove.__code__.co_filename, "exec")
+            scope = {}
+            exec(code, bs.__dict__, scope)
+            saved["globals"].append((bs, _COMB_HOOK, bs.__dict__.get(_COMB_HOOK, _MISSING)))
+            # DEBUG keeps the reference's own block (it prints and asserts degree bounds on the way)
+            bs.__dict__[_COMB_HOOK] = lambda *args: (None if os.environ.get("DEBUG") is not None
+                                                     else glue.combination_codeword(*args))
+            guarded = scope["prove"]
+
+            def prove(self, *args, **kwargs):
+                with glue.keep_planes():  # codewords stay readable on the device for the length of one proof
+                    return guarded(self, *args, **kwargs)
+            prove.__wrapped__ = guarded
+            prove.__doc__ = guarded.__doc__
+            set_attr(bs.BrainfuckStark, "prove", prove)
+        except (ImportError, LookupError, OSError, SyntaxError) as e:
+            warnings.warn("nonlinear combination stays on the host: %s" % e)
+
     _state = {"glue": glue, "saved": saved, "mods": mods}
     return glue
 
@@ -132,7 +189,10 @@ def uninstall():
         return
     saved = _state["saved"]
     for mod, name, orig in saved["globals"]:
-        mod.__dict__[name] = orig
+        if orig is _MISSING:
+            mod.__dict__.pop(name, None)
+        else:
+            mod.__dict__[name] = orig
     for obj, name, orig in reversed(saved["attrs"]):
         if orig is _MISSING:
             delattr(obj, name)

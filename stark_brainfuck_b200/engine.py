@@ -199,6 +199,26 @@ class Engine:
                                           omega, _ptr(out), C.byref(flag), self.stream_ptr()))
         return out, bool(flag.value)
 
+    # ---- nonlinear combination --------------------------------
+    def combination(self, columns, wa, wb, shifts, N, offset, omega):
+        """code/brainfuck_stark.py:241-298: sum_c (wa_c + wb_c x^shift_c) col_c over the domain offset*omega^j.
+        columns: device tensors (1, N) (base field) or (3, N); wa, wb: (n_cols, 3) uint64; shifts: (n_cols,).
+        Returns (3, N) planes."""
+        n = len(columns)
+        ptrs = np.array([t.data_ptr() for t in columns], dtype=np.uint64)
+        strides = np.array([t.stride(0) if t.shape[0] > 1 else N for t in columns], dtype=np.uint64)
+        planes = np.array([t.shape[0] for t in columns], dtype=np.uint32)
+        for t in columns:
+            assert t.dtype == torch.int64 and t.shape[1] == N and t.stride(1) == 1
+        wa = np.ascontiguousarray(wa, dtype=np.uint64).reshape(n, 3)
+        wb = np.ascontiguousarray(wb, dtype=np.uint64).reshape(n, 3)
+        shifts = np.ascontiguousarray(shifts, dtype=np.uint64).reshape(n)
+        out = self.empty(3, N)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        self.check(self.lib.b2s_combination(vp(ptrs), vp(strides), vp(planes), vp(wa), vp(wb), vp(shifts), n, N, offset,
+                                            omega, _ptr(out), out.stride(0), self.stream_ptr()))
+        return out
+
     def gather(self, planes, indices):
         """planes[:, indices] to the host as numpy (len(indices), q) uint64"""
         q, n = planes.shape

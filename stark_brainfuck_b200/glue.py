@@ -10,6 +10,7 @@ Argument meaning, return types, error behaviour (AssertionError / IndexError) an
 object identity graph that pickle observes follow the reference; see the per-function
 citations.  All heavy arithmetic happens in libb2s.so through `Engine`.
 """
+import contextlib
 import pickle
 
 import numpy as np
@@ -27,6 +28,7 @@ class Glue:
         self._engine = engine
         self._xtpl = {}  # id(xfield) -> (xfield, templates)
         self._btpl = {}  # id(field)  -> (field, templates)
+        self._kept = None  # id(list) -> (list, device planes, first, last) inside keep_planes()
 
     @property
     def engine(self):
@@ -71,9 +73,39 @@ class Glue:
             return self.engine.upload(self.B.bfe_to_np(values)), "b", first.field
         raise TypeError("cannot transform a list of %r" % type(first))
 
-    def _from_device(self, t, kind, field):
+    def _from_device(self, t, kind, field, keep=False):
         a = self.engine.download(t)
-        return self.B.np_to_xfe(a, field) if kind == "x" else self.B.np_to_bfe(a[0], field)
+        values = self.B.np_to_xfe(a, field) if kind == "x" else self.B.np_to_bfe(a[0], field)
+        if keep:  # a codeword that a later device op (nonlinear combination) can read without marshalling
+            self.remember_planes(values, t)
+        return values
+
+    # Codeword lists must stay plain lists (pickle writes a subclass differently), so the link from a
+    # returned list to the device planes it was read from is a side table.  It only exists inside
+    # keep_planes() -- the drop-in opens it around BrainfuckStark.prove, whose code is known not to
+    # mutate its codewords in place -- and holds the lists strongly, so ids cannot be recycled.
+    @contextlib.contextmanager
+    def keep_planes(self):
+        outer, self._kept = self._kept, {}
+        try:
+            yield self
+        finally:
+            self._kept = outer
+
+    def remember_planes(self, values, planes):
+        if self._kept is not None and len(values):
+            self._kept[id(values)] = (values, planes, values[0], values[-1])
+
+    def planes_of(self, codeword):
+        """device planes behind a codeword, or None"""
+        if isinstance(codeword, DeviceCodeword):
+            return codeword._planes
+        ent = self._kept.get(id(codeword)) if self._kept is not None else None
+        if ent is None or ent[0] is not codeword or len(codeword) != ent[1].shape[1]:
+            return None
+        if codeword[0] is not ent[2] or codeword[-1] is not ent[3]:
+            return None
+        return ent[1]
 
     # ------------------------------------------------------------------ code/ntt.py
     def _transform(self, primitive_root, values, inverse, offset=1, n_out=None, lone_source=None):
@@ -101,7 +133,7 @@ class Glue:
             base = self.B.np_to_xfe(self.engine.download(out)[:, :share], first.field)
             X = self.B.ExtensionFieldElement
             return [X(base[i % share].polynomial, first.field) for i in range(n)]
-        return self._from_device(out, kind, first.field)
+        return self._from_device(out, kind, first.field, keep=True)
 
     @staticmethod
     def _shared_output_period(arr, n):
@@ -250,7 +282,7 @@ class Glue:
             raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
         out = self.engine.ntt(d, _ilog2(n), w, offset=off)
         # scaled coefficients take offset.field (code/univariate.py:169); ntt keeps values[0].field
-        return self._from_device(out, kind, dom.offset.field if kind == "b" else coeffs[0].field)
+        return self._from_device(out, kind, dom.offset.field if kind == "b" else coeffs[0].field, keep=True)
 
     def domain_xevaluate(self, dom, polynomial, xfield=None):
         """code/fri.py:32-37"""
@@ -307,7 +339,55 @@ class Glue:
         # code/ntt.py:178-179
         assert not vanishes, "batch inverse does not work when input contains a zero"
         a = self.engine.download(out.reshape(-1, N)).reshape(-1, 3, N)
-        return [self.B.np_to_xfe(a[c], xfield) for c in range(a.shape[0])]
+        res = [self.B.np_to_xfe(a[c], xfield) for c in range(a.shape[0])]
+        for c, values in enumerate(res):
+            self.remember_planes(values, out[c])
+        return res
+
+    # ------------------------------------------------------------------ code/brainfuck_stark.py:241-298
+    def combination_codeword(self, domain, xfield, max_degree, randomizer_codeword, base_codewords, base_degree_bounds,
+                             extension_codewords, extension_degree_bounds, quotient_codewords,
+                             quotient_degree_bounds, weights):
+        """The nonlinear combination of code/brainfuck_stark.py:241-298 as one device op: every codeword
+        contributes weight * c and weight' * (x^shift * c), shift = max_degree - degree bound.  Codewords
+        that came out of device ops inside keep_planes() are read where they are; other lists are
+        marshalled.  Returns a DeviceCodeword (the list the reference builds, materialised lazily),
+        or None when the result's object graph could not be guaranteed (non-canonical weights): the
+        caller then runs the reference's own block."""
+        B = self.B
+        N = domain.length
+        n_terms = 1 + 2 * (len(base_codewords) + len(extension_codewords) + len(quotient_codewords))
+        # code/brainfuck_stark.py:246-247, :258-259, :270-271, :294-295
+        assert len(base_codewords) == len(base_degree_bounds) and len(extension_codewords) == len(extension_degree_bounds)
+        assert len(quotient_codewords) == len(quotient_degree_bounds)
+        assert n_terms == len(weights), f"number of terms {n_terms} is not equal to number of weights {len(weights)}"
+        if N < 2 or not all(B.is_xfe(w) for w in weights) or not B.xfe_canonical(weights, xfield):
+            return None
+        columns, shifts = [], [0]
+        bounds = list(base_degree_bounds) + list(extension_degree_bounds) + list(quotient_degree_bounds)
+        for k, cw in enumerate([randomizer_codeword] + list(base_codewords) + list(extension_codewords) +
+                               list(quotient_codewords)):
+            if len(cw) != N:
+                return None
+            planes = self.planes_of(cw)
+            if planes is None:
+                if B.is_xfe(cw[0]):
+                    planes = self.engine.upload(B.xfe_to_np(cw))
+                elif B.is_bfe(cw[0]):
+                    planes = self.engine.upload(B.bfe_to_np(cw))
+                else:
+                    return None
+            columns.append(planes)
+            if k:
+                shift = max_degree - bounds[k - 1]
+                if shift < 0:
+                    return None
+                shifts.append(shift)
+        w = B.xfe_to_np(weights).T  # (n_terms, 3)
+        wa = np.concatenate([w[:1], w[1::2]])
+        wb = np.concatenate([np.zeros((1, 3), dtype=np.uint64), w[2::2]])
+        out = self.engine.combination(columns, wa, wb, shifts, N, domain.offset.value, domain.omega.value)
+        return DeviceCodeword(self, out, xfield)
 
     def table_boundary_quotients(self, table, fri_domain, codewords, challenges):
         """code/table.py:155-178"""
@@ -342,6 +422,9 @@ class Glue:
         """Body of Merkle.__init__ (code/merkle.py:8-41).  Sets the public attributes
         num_leafs, depth, leafs, nodes on `tree`."""
         n = len(data_array)
+        if isinstance(data_array, DeviceCodeword) and leaf_cache is None and n > 0 and n & (n - 1) == 0:
+            # a codeword that never left the device: its lazily materialised elements ARE the leaves
+            leaf_cache, device_planes, canonical = data_array, data_array._planes, True
         tree.num_leafs = n
         npo2 = 1
         while npo2 < n:
@@ -385,6 +468,9 @@ class Glue:
         pickles them and the device hashes the byte strings and builds the tree (b2s_merkle_blobs).
         open / verify / root stay the reference's: they only index .leafs and .nodes."""
         n = len(data_array)
+        if isinstance(data_array, DeviceCodeword) and leaf_cache is None and n > 0 and n & (n - 1) == 0:
+            # a codeword that never left the device: its lazily materialised elements ARE the leaves
+            leaf_cache, device_planes, canonical = data_array, data_array._planes, True
         tree.num_leafs = n
         npo2 = 1
         while npo2 < n:
@@ -412,11 +498,14 @@ class Glue:
         trees, codewords = [], []
 
         N = len(codeword)
-        canonical = N > 0 and (N & (N - 1)) == 0 and B.is_xfe(codeword[0]) and B.xfe_canonical(codeword, xfield)
-        if N > 0 and not B.is_xfe(codeword[0]):
-            # code/fri.py:127: (one + alpha / ...) * codeword[i] needs extension-field elements
-            raise AttributeError("%r object has no attribute 'polynomial'" % type(codeword[0]).__name__)
-        planes = eng.upload(B.xfe_to_np(codeword)) if N > 0 else None
+        if isinstance(codeword, DeviceCodeword) and N > 0 and (N & (N - 1)) == 0:
+            canonical, planes = True, codeword._planes  # e.g. the nonlinear combination: already on the device
+        else:
+            canonical = N > 0 and (N & (N - 1)) == 0 and B.is_xfe(codeword[0]) and B.xfe_canonical(codeword, xfield)
+            if N > 0 and not B.is_xfe(codeword[0]):
+                # code/fri.py:127: (one + alpha / ...) * codeword[i] needs extension-field elements
+                raise AttributeError("%r object has no attribute 'polynomial'" % type(codeword[0]).__name__)
+            planes = eng.upload(B.xfe_to_np(codeword)) if N > 0 else None
         nodes = None
         cache = None  # identity-stable objects of the current (device) codeword
         for r in range(num_rounds):

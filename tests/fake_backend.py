@@ -166,6 +166,20 @@ class FakeLib:
         h_flag._obj.value = int(flag)
         return 0
 
+    def b2s_combination(self, h_cols, h_strides, h_planes, h_wa, h_wb, h_shifts, n_cols, N, offset, omega, d_out,
+                        out_stride, stream):
+        self.launches += 1
+        ptrs = _u64(_addr(h_cols), n_cols)
+        strides = _u64(_addr(h_strides), n_cols)
+        planes = np.ctypeslib.as_array((C.c_uint32 * n_cols).from_address(_addr(h_planes)))
+        cols = [np.stack([_u64(int(ptrs[c]) + 8 * int(strides[c]) * q, N) for q in range(int(planes[c]))])
+                for c in range(n_cols)]
+        out = orc.combination(cols, _u64(_addr(h_wa), 3 * n_cols), _u64(_addr(h_wb), 3 * n_cols),
+                              _u64(_addr(h_shifts), n_cols), offset, omega)
+        for q in range(3):
+            _u64(_addr(d_out) + 8 * out_stride * q, N)[:] = out[q]
+        return 0
+
     def b2s_dist_twiddle_transpose(self, d_in, in_stride, rows, cols, row_base, omega, tw_mul, out_ptrs, n_peers,
                                    out_row_stride, out_col_offset, stream):
         self.launches += 1

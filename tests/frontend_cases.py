@@ -274,3 +274,52 @@ def case_fri_errors(env):
         fri = env.Fri(f.generator(), f.primitive_nth_root(8), 8, 4, 8, xf)
         cw, _ = fri_input(env, 3, 4, 203)
         fri.prove(cw, env.ProofStream())
+
+
+def case_combination(env, glue):
+    """the nonlinear combination block of BrainfuckStark.prove (code/brainfuck_stark.py:241-298)
+    against the outputs of the reference's own statements (tests/golden/combination.json): values, the
+    pickle of the resulting list (object graph and field identities) and the Merkle root over it."""
+    from stark_brainfuck_b200.glue import DeviceCodeword
+    for c in golden("combination.json")["cases"]:
+        N = c["N"]
+        dom = env.Fri.Domain(env.field(c["offset"]), env.field(c["omega"]), N)
+        rnd = [X(env, *t) for t in c["randomizer"]]
+        base = [[env.BaseFieldElement(v, env.field) for v in col] for col in c["base"]]
+        ext = [[X(env, *t) for t in col] for col in c["extension"]]
+        quo = [[X(env, *t) for t in col] for col in c["quotient"]]
+        weights = [X(env, *t) for t in c["weights"]]
+        args = (c["base_degree_bounds"], c["extension_degree_bounds"], c["quotient_degree_bounds"])
+        for attach in (False, True):
+            scope = glue.keep_planes()
+            scope.__enter__()
+            if attach:  # codewords that still have their device planes (what the drop-in's own ops return)
+                up = glue.engine.upload
+                for col in base:
+                    glue.remember_planes(col, up(np.array(vals(col), dtype=np.uint64)))
+                for col in ext + quo:
+                    glue.remember_planes(col, up(np.array(triples(col), dtype=np.uint64).T.copy()))
+                assert all(glue.planes_of(col) is not None for col in base + ext + quo)
+            out = glue.combination_codeword(dom, env.xfield, c["max_degree"], rnd, base, args[0], ext, args[1], quo,
+                                            args[2], weights)
+            assert isinstance(out, DeviceCodeword) and len(out) == N
+            tree = env.Merkle(out)
+            assert tree.root().hex() == c["root"]
+            assert tree.leafs[3] is out[3]  # the tree serves the codeword's own (lazily built) objects
+            assert triples(out[5:7]) == c["out"][5:7]
+            full = out.materialize()
+            assert triples(full) == c["out"]
+            assert hashlib.sha256(pickle.dumps(full)).hexdigest() == c["out_pickle_sha256"]
+            if attach and quo:  # a list whose ends were replaced is not read from its stale planes
+                quo[0][0] = X(env, 1, 2, 3)
+                assert glue.planes_of(quo[0]) is None
+                quo[0][0] = X(env, *c["quotient"][0][0])
+            scope.__exit__(None, None, None)
+            assert all(glue.planes_of(col) is None for col in base + ext + quo)  # nothing outlives the scope
+        # weights whose coefficients carry a foreign field object: the reference's result would carry it too
+        odd = [env.ExtensionFieldElement(env.Polynomial([env.BaseFieldElement(5, env.field)]), env.xfield)] + weights[1:]
+        assert glue.combination_codeword(dom, env.xfield, c["max_degree"], rnd, base, args[0], ext, args[1], quo, args[2],
+                                         odd) is None
+        with pytest.raises(AssertionError):
+            glue.combination_codeword(dom, env.xfield, c["max_degree"], rnd, base, args[0], ext, args[1], quo, args[2],
+                                      weights[:-1])

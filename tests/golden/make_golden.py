@@ -11,7 +11,7 @@ little-endian u64 values; ExtensionFieldElement = c0,c1,c2 with trimmed
 coefficients zero-filled, elements in list order.
 
 Usage:  python tests/golden/make_golden.py <group> [...]
-Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients
+Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination
 Heavy groups are meant to run in the background, one process each.
 """
 import hashlib
@@ -543,6 +543,70 @@ def group_quotients():
     dump("quotients.json", out)
 
 
+def group_combination():
+    """the nonlinear combination block of BrainfuckStark.prove
+    (code/brainfuck_stark.py:241-298).  The block is inline, so the reference's OWN statements are cut
+    out of the source of prove() at run time (between its two marker comments) and executed on toy
+    inputs; nothing is restated here.  Inputs are stored in full."""
+    import inspect
+    import textwrap
+    from functools import reduce
+    import brainfuck_stark
+    src = inspect.getsource(brainfuck_stark.BrainfuckStark.prove)
+    a = src.index("# compute terms of nonlinear combination polynomial")
+    b = src.index("# commit to combination codeword")
+    a = src.rindex("\n", 0, a) + 1
+    b = src.rindex("\n", 0, b) + 1
+    block = textwrap.dedent(src[a:b])
+    R = random.Random(4242)
+    out = {"cases": []}
+    for N, nb, ne, nq, max_degree in ((64, 3, 2, 3, 40), (32, 1, 0, 1, 9), (16, 0, 1, 0, 5)):
+        dom = Fri.Domain(field.generator(), field.primitive_nth_root(N), N)
+
+        def rx():
+            return X(R.randrange(P), R.randrange(P), R.randrange(P))
+
+        class Stub:
+            pass
+        me = Stub()
+        me.xfield, me.max_degree, me.fri = xfield, max_degree, Stub()
+        me.fri.domain = dom
+        base = [[BaseFieldElement(R.randrange(P), field) for _ in range(N)] for _ in range(nb)]
+        ext = [[rx() for _ in range(N)] for _ in range(ne)]
+        quo = [[rx() for _ in range(N)] for _ in range(nq)]
+        rnd = [rx() for _ in range(N)]
+        if nb:
+            base[0][1] = field.zero()
+        if ne:
+            ext[0][2] = xfield.zero()
+            ext[-1][3] = X(5)
+        if nq:
+            quo[0][0] = X(0, 7)
+        bdb = [R.randrange(0, max_degree + 1) for _ in range(nb)]
+        edb = [R.randrange(0, max_degree + 1) for _ in range(ne)]
+        qdb = [R.randrange(0, max_degree + 1) for _ in range(nq)]
+        if nq:
+            qdb[-1] = max_degree  # shift 0
+        weights = [rx() for _ in range(1 + 2 * (nb + ne + nq))]
+        if nb:
+            weights[2] = xfield.zero()
+        ns = {"self": me, "os": os, "reduce": reduce, "randomizer_codeword": rnd, "base_codewords": base,
+              "num_base_polynomials": nb, "base_degree_bounds": bdb, "extension_codewords": ext,
+              "num_extension_polynomials": ne, "extension_degree_bounds": edb, "quotient_codewords": quo,
+              "num_quotient_polynomials": nq, "quotient_degree_bounds": qdb, "weights": weights}
+        exec(compile(block, "brainfuck_stark.py:241-298", "exec"), ns)
+        comb = ns["combination_codeword"]
+        out["cases"].append({
+            "N": N, "offset": dom.offset.value, "omega": dom.omega.value, "max_degree": max_degree,
+            "randomizer": [xfe_triple(x) for x in rnd], "base": [[v.value for v in c] for c in base],
+            "extension": [[xfe_triple(x) for x in c] for c in ext], "quotient": [[xfe_triple(x) for x in c] for c in quo],
+            "base_degree_bounds": bdb, "extension_degree_bounds": edb, "quotient_degree_bounds": qdb,
+            "weights": [xfe_triple(x) for x in weights], "out": [xfe_triple(x) for x in comb],
+            "out_pickle_sha256": hashlib.sha256(pickle.dumps(comb)).hexdigest(),
+            "root": Merkle(comb).root().hex()})
+    dump("combination.json", out)
+
+
 if __name__ == "__main__":
     for grp in sys.argv[1:]:
         if grp == "small":
@@ -557,6 +621,8 @@ if __name__ == "__main__":
             group_xntt_big()
         elif grp == "bfs":
             group_bfs()
+        elif grp == "combination":
+            group_combination()
         elif grp == "quotients":
             group_quotients()
         else:

@@ -276,3 +276,31 @@ def test_salted_merkle_matches_reference(reference_dropin):
     assert got == want
     with pytest.raises(AssertionError):
         salted_merkle.SaltedMerkle([])
+
+
+def test_nonlinear_combination_matches_reference_block(env):
+    """SURVEY 8(f) row 3 against the outputs of the reference's own statements"""
+    fc.case_combination(env, env.glue)
+
+
+def test_prove_is_recompiled_with_guarded_combination_block(env, monkeypatch):
+    """install() recompiles BrainfuckStark.prove from the reference's own source with the combination
+    block guarded by the hook; the block itself stays as the fallback (DEBUG, or a hook returning None)"""
+    import inspect
+    import brainfuck_stark
+    from stark_brainfuck_b200 import dropin
+    assert dropin.installed()
+    prove = brainfuck_stark.BrainfuckStark.prove.__wrapped__  # under the keep_planes() scope
+    assert inspect.getsourcefile(prove).endswith("brainfuck_stark.py")
+    assert dropin._COMB_HOOK in prove.__code__.co_names and dropin._COMB_HOOK in brainfuck_stark.__dict__
+    assert "terms" in prove.__code__.co_varnames  # the reference's block is still compiled in
+    hook = brainfuck_stark.__dict__[dropin._COMB_HOOK]
+    monkeypatch.setenv("DEBUG", "1")
+    assert hook(None) is None  # DEBUG: reference block runs, nothing else is touched
+    monkeypatch.delenv("DEBUG")
+
+    class Moved:
+        def prove(self):
+            pass
+    with pytest.raises(LookupError):
+        dropin.guarded_prove_source(Moved.prove)

@@ -331,3 +331,42 @@ def test_ntt_three_pass_plan(eng):
     y = eng.ntt(d, logn, w)
     assert np.array_equal(eng.download(y)[0], orc.ntt(w, x))
     assert np.array_equal(eng.download(eng.ntt(y, logn, w, inverse=True))[0], x)
+
+
+def test_combination_golden_and_oracle(eng):
+    """SURVEY 8(f) row 3 through the C ABI: the reference's golden combination codewords, then random column
+    sets (base and extension columns, strided views, repeated and zero shifts, zero weights) against the oracle."""
+    from util import combination_cases
+    for cols, wa, wb, shifts, N, offset, omega, want in combination_cases(golden("combination.json")):
+        out = eng.combination([eng.upload(c) for c in cols], wa, wb, shifts, N, offset, omega)
+        assert np.array_equal(eng.download(out), want)
+    R = random.Random(78)
+    for logn, n_cols in ((4, 3), (9, 7), (10, 12), (13, 40), (16, 9)):
+        N = 1 << logn
+        w = root_of_unity(logn)
+        host, dev = [], []
+        big = eng.upload(rand_xfe(900 + logn, 2 * N))  # extension columns as views into a wider buffer (stride 2N)
+        for c in range(n_cols):
+            if c == 0:
+                h = eng.download(big)[:, N // 2:N // 2 + N].copy()
+                d = big[:, N // 2:N // 2 + N]
+            elif c % 3 == 1:
+                h = rand_bfe(910 + logn + c, N).reshape(1, N)
+                d = eng.upload(h)
+            else:
+                h = rand_xfe(920 + logn + c, N)
+                d = eng.upload(h)
+            host.append(h)
+            dev.append(d)
+        wa = np.array([[R.randrange(P) for _ in range(3)] for _ in range(n_cols)], dtype=np.uint64)
+        wb = np.array([[R.randrange(P) for _ in range(3)] for _ in range(n_cols)], dtype=np.uint64)
+        wb[0] = 0
+        wa[1] = 0
+        shifts = [R.choice([0, 1, 5, N // 4 + 3, N - 1, 3 * N + 1]) for _ in range(n_cols)]
+        out = eng.combination(dev, wa, wb, shifts, N, 7, w)
+        assert np.array_equal(eng.download(out), orc.combination(host, wa, wb, shifts, 7, w)), logn
+    out = eng.combination([], np.zeros((0, 3)), np.zeros((0, 3)), [], 16, 7, root_of_unity(4))
+    assert not eng.download(out).any()
+    from stark_brainfuck_b200._lib import B2SError
+    with pytest.raises(B2SError):
+        eng.combination([eng.upload(rand_bfe(1, 12))], np.zeros((1, 3)), np.zeros((1, 3)), [0], 12, 7, 1)

@@ -63,3 +63,7 @@ def test_fri_big_transcripts(env, logn):
     if os.path.isdir(out):  # keep the proof so the authoring container can feed it to the real reference verifier
         with open(os.path.join(out, "fri_%d_transcript.bin" % logn), "wb") as f:
             f.write(ser)
+
+
+def test_nonlinear_combination(env, mirror_gpu):
+    fc.case_combination(env, mirror_gpu.glue())

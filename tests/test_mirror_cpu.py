@@ -59,3 +59,7 @@ def test_mirror_field_arithmetic(env):
         assert fc.triples([env.xfield.sample(seed)]) == [c["xfe"]] and f.sample(seed).value == c["bfe"]
     for k, v in S["roots"].items():
         assert f.primitive_nth_root(1 << int(k)).value == v
+
+
+def test_nonlinear_combination(env, mirror_cpu):
+    fc.case_combination(env, mirror_cpu.glue())

@@ -81,3 +81,19 @@ def quotient_cases(g):
     prog = quotient_program([[[[1, 0], [1, 0, 0]], [[0, 1], [P - 1, 0, 0]]]])
     yield ("permutation", np.stack([lhs, rhs]).copy(), 0, prog, 1, 0, 1,
            np.array(pm["out"], dtype=np.uint64).T.reshape(1, 3, N))
+
+
+def combination_cases(g):
+    """tests/golden/combination.json -> (columns, wa, wb, shifts, N, offset, omega, want (3, N)) per case, in the
+    argument convention of b2s_combination / orc_combination"""
+    for c in g["cases"]:
+        N = c["N"]
+        cols = [np.array(c["randomizer"], dtype=np.uint64).T.copy()]
+        cols += [np.array(col, dtype=np.uint64).reshape(1, N) for col in c["base"]]
+        cols += [np.array(col, dtype=np.uint64).T.copy() for col in c["extension"] + c["quotient"]]
+        bounds = c["base_degree_bounds"] + c["extension_degree_bounds"] + c["quotient_degree_bounds"]
+        w = np.array(c["weights"], dtype=np.uint64)
+        wa = np.concatenate([w[:1], w[1::2]])
+        wb = np.concatenate([np.zeros((1, 3), dtype=np.uint64), w[2::2]])
+        shifts = [0] + [c["max_degree"] - b for b in bounds]
+        yield cols, wa, wb, shifts, N, c["offset"], c["omega"], np.array(c["out"], dtype=np.uint64).T.copy()
