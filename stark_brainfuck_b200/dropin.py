@@ -66,11 +66,12 @@ def guarded_prove_source(prove):
     return src[:a] + call + textwrap.indent(block, "    ") + src[b:]
 
 
-def install(reference_dir=None, engine=None, quotients=True, salted=True, combination=True):
+def install(reference_dir=None, engine=None, quotients=True, salted=True, combination=True, lde=True):
     """Patch the reference modules importable from `reference_dir` (or already on sys.path).
     `quotients=True` also moves the quotient-codeword loops of table.py / permutation_argument.py
     (93 % of prove()) to the device, `salted=True` the trees of salted_merkle.py,
-    `combination=True` the nonlinear combination inside BrainfuckStark.prove (see module docstring).
+    `combination=True` the nonlinear combination inside BrainfuckStark.prove (see module docstring),
+    `lde=True` Table.interpolate_columns / lde / ldex as batched transforms over all columns of a table.
     Returns the Glue in use."""
     global _state
     if _state is not None:
@@ -147,6 +148,25 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
         # `urandom` is looked up in the module at call time: tests patch salted_merkle.urandom
         set_attr(sm.SaltedMerkle, "__init__",
                  lambda self, data_array: glue.salted_merkle_build(self, data_array, lambda k: sm.urandom(k)))
+
+    # -- 5b. next row: interpolate_columns + lde/ldex, all columns of a table at once ---
+    if lde:
+        table = importlib.import_module("table")
+        T = table.Table
+        draw = lambda k: table.os.urandom(k)  # noqa: E731  (looked up at call time: tests seed os.urandom)
+        set_attr(T, "interpolate_columns", lambda self, omega, omega_order, column_indices:
+                 glue.table_interpolate_columns(self, omega, omega_order, column_indices, draw))
+
+        def lde_(self, domain):
+            self.codewords = glue.table_lde(self, domain, draw)
+            return self.codewords
+
+        def ldex_(self, domain, xfield):
+            codewords = glue.table_lde(self, domain, draw, xfield=xfield)
+            self.codewords += codewords
+            return codewords
+        set_attr(T, "lde", lde_)
+        set_attr(T, "ldex", ldex_)
 
     # -- 6. next row: the nonlinear combination inside BrainfuckStark.prove -------
     if combination:

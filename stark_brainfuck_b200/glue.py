@@ -14,6 +14,7 @@ import contextlib
 import pickle
 
 import numpy as np
+import torch
 
 from .engine import P, default_engine
 
@@ -108,7 +109,7 @@ class Glue:
         return ent[1]
 
     # ------------------------------------------------------------------ code/ntt.py
-    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None, lone_source=None):
+    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None, lone_source=None, res_field=None):
         n = len(values) if n_out is None else n_out
         w = self.base_value(primitive_root, "primitive_root")
         # every 2-power root of unity of F_p^3 lies in F_p, so a root with higher
@@ -121,6 +122,8 @@ class Glue:
             arr, kind = self.B.bfe_to_np(values).reshape(1, -1), "b"
         else:
             raise TypeError("cannot transform a list of %r" % type(first))
+        if res_field is None:
+            res_field = first.field  # ntt keeps values[0].field (code/ntt.py:20-23)
         share = 0
         if kind == "x" and not inverse:
             share = self._shared_output_period(arr, n)
@@ -130,10 +133,10 @@ class Glue:
         if share:
             # outputs i and i + share are the same sub-transform output with a zero odd partner all the
             # way up: distinct elements wrapping the SAME coefficient objects (see _lone_coefficient_ntt)
-            base = self.B.np_to_xfe(self.engine.download(out)[:, :share], first.field)
+            base = self.B.np_to_xfe(self.engine.download(out)[:, :share], res_field)
             X = self.B.ExtensionFieldElement
-            return [X(base[i % share].polynomial, first.field) for i in range(n)]
-        return self._from_device(out, kind, first.field, keep=True)
+            return [X(base[i % share].polynomial, res_field) for i in range(n)]
+        return self._from_device(out, kind, res_field, keep=True)
 
     @staticmethod
     def _shared_output_period(arr, n):
@@ -205,7 +208,9 @@ class Glue:
         if self.B.is_xfe(coeffs[0]) and self.B.is_xfe(offset) and not coeffs[0].is_zero() \
                 and all(c.is_zero() for c in coeffs[1:]):
             lone = (offset ^ 0) * coeffs[0]  # the scaled constant term, built by the caller's own classes
-        return self._transform(generator, coeffs, False, offset=off, n_out=order, lone_source=lone)
+        # the scaled coefficients (offset ^ i) * c carry offset.field (code/univariate.py:169), ntt keeps it
+        return self._transform(generator, coeffs, False, offset=off, n_out=order, lone_source=lone,
+                               res_field=offset.field)
 
     def fast_coset_interpolate(self, offset, generator, values):
         """code/ntt.py:171-174: intt, then scale by offset^-1; all n coefficients are kept"""
@@ -299,6 +304,134 @@ class Glue:
         """code/fri.py:42-44"""
         xfield = values[0].field
         return self.fast_coset_interpolate(xfield.lift(dom.offset), xfield.lift(dom.omega), values)
+
+    # ------------------------------------------------------------------ code/table.py:112-149 (next row 2)
+    def _interpolated_planes(self, table, omega, omega_order, column_indices, urandom):
+        """Coefficient planes of Table.interpolate_columns (code/table.py:112-136) for all requested columns
+        at once.  The interpolant through the `height` trace points (on the subgroup <omicron>) and the
+        `num_randomizers` extra points omega^(2i+1) is unique, so it is computed as
+            f = f0 + (x^height - 1) * q,   f0 = intt_omicron(trace),   q through (rho_k, (r_k - f0(rho_k)) / (rho_k^height - 1))
+        instead of the reference's recursive fast_interpolate.  Randomizers are drawn exactly like the
+        reference draws them (per column, table.field.sample(urandom(24))), so seeded runs stay byte-identical.
+        Returns (planes (ncols * pl, height + nr) on the device, pl, kind, first trace element)."""
+        B, eng = self.B, self.engine
+        # code/table.py:113-114
+        assert omega.has_order_po2(omega_order), "omega does not have claimed order"
+        h, nr = table.height, table.num_randomizers
+        cols = list(column_indices)
+        traces, rand_vals = [], []
+        for c in cols:
+            trace = [row[c] for row in table.matrix]
+            randomizers = [table.field.sample(urandom(3 * 8)) for _ in range(nr)]
+            # code/table.py:129-130
+            assert len(trace) + nr == h + nr, f"length of domain {h + nr} and values {len(trace) + nr} are unequal"
+            traces.append(trace)
+            rand_vals.append(randomizers)
+        first = traces[0][0]
+        if B.is_xfe(first):
+            kind, pl = "x", 3
+            arr = np.concatenate([B.xfe_to_np(t) for t in traces])
+            rv = [[[co.value for co in r.polynomial.coefficients] + [0] * (3 - len(r.polynomial.coefficients))
+                   for r in rs] for rs in rand_vals]
+        elif B.is_bfe(first):
+            kind, pl = "b", 1
+            arr = np.stack([B.bfe_to_np(t) for t in traces])
+            rv = [[[r.value] for r in rs] for rs in rand_vals]
+        else:
+            raise TypeError("cannot interpolate a column of %r" % type(first))
+        omicron = table.omicron.value
+        buf = torch.zeros((len(cols) * pl, h + nr), dtype=torch.int64, device=eng.device)
+        f0 = buf[:, :h]
+        if h > 1:
+            eng.ntt(eng.upload(arr), _ilog2(h), omicron, inverse=True, out=f0)
+        else:
+            f0.copy_(eng.upload(arr))
+        if nr:
+            w = omega.value
+            rho = [pow(w, 2 * k + 1, P) for k in range(nr)]
+            zinv = [pow((pow(r, h, P) - 1) % P, P - 2, P) for r in rho]  # rho is an odd power: not on the subgroup
+            pts = eng.upload(np.array(rho, dtype=np.uint64))
+            # basis polynomials of the nr extra points (base field, tiny): L_k(x) = prod_{j != k} (x - rho_j) / (rho_k - rho_j)
+            basis = []
+            for k in range(nr):
+                poly, den = [1], 1
+                for j in range(nr):
+                    if j != k:
+                        poly = [(a - rho[j] * b) % P for a, b in zip([0] + poly, poly + [0])]
+                        den = den * (rho[k] - rho[j]) % P
+                dinv = pow(den, P - 2, P)
+                basis.append([c * dinv % P for c in poly])
+            fix = np.zeros((len(cols) * pl, 2 * nr), dtype=np.uint64)  # new values of coefficients [0, nr) and [h, h + nr)
+            low = eng.download(buf[:, :nr])
+            for ci in range(len(cols)):
+                at_rho = eng.download(eng.eval_points(f0[ci * pl:(ci + 1) * pl], pts))  # (pl, nr)
+                for s_ in range(pl):
+                    t = [(rv[ci][k][s_] - int(at_rho[s_, k])) * zinv[k] % P for k in range(nr)]
+                    q = [sum(t[k] * basis[k][i] for k in range(nr)) % P for i in range(nr)]
+                    for i in range(nr):
+                        fix[ci * pl + s_, i] = (int(low[ci * pl + s_, i]) - q[i]) % P
+                        fix[ci * pl + s_, nr + i] = q[i]
+            fixd = eng.upload(fix)
+            if h >= nr:
+                buf[:, :nr] = fixd[:, :nr]
+                buf[:, h:] = fixd[:, nr:]
+            else:  # fewer trace points than randomizers: the two ranges overlap, add instead
+                raise NotImplementedError("more randomizers than rows")
+        return buf, pl, kind, first
+
+    def table_interpolate_columns(self, table, omega, omega_order, column_indices, urandom):
+        """code/table.py:112-136"""
+        Pn = self.B.Polynomial
+        if table.height == 0:
+            assert omega.has_order_po2(omega_order), "omega does not have claimed order"
+            return [Pn([])] * len(column_indices)
+        if len(column_indices) == 0:
+            assert omega.has_order_po2(omega_order), "omega does not have claimed order"
+            return []
+        buf, pl, kind, first = self._interpolated_planes(table, omega, omega_order, column_indices, urandom)
+        a = self.engine.download(buf)
+        if kind == "b":
+            return [Pn(self.B.np_to_bfe(a[c], first.field)) for c in range(a.shape[0])]
+        return [Pn(self.B.np_to_xfe(a[3 * c:3 * c + 3], first.field)) for c in range(a.shape[0] // 3)]
+
+    def table_lde(self, table, domain, urandom, xfield=None, columns=None):
+        """code/table.py:138-148: lde (xfield None: columns [0, base_width), Domain.evaluate) and ldex (columns
+        [base_width, full_width), Domain.xevaluate) -- interpolation and coset evaluation of all columns of the
+        table as two batched device transforms.  Returns the list of codewords (the caller stores them)."""
+        B, eng = self.B, self.engine
+        if columns is None:
+            columns = range(table.base_width) if xfield is None else range(table.base_width, table.full_width)
+        Pn = self.B.Polynomial
+        if table.height == 0 or len(columns) == 0 or domain.length <= 1:
+            polys = self.table_interpolate_columns(table, domain.omega, domain.length, columns, urandom)
+            return [self.domain_evaluate(domain, p) if xfield is None else self.domain_xevaluate(domain, p, xfield)
+                    for p in polys]
+        buf, pl, kind, first = self._interpolated_planes(table, domain.omega, domain.length, columns, urandom)
+        N, m = domain.length, buf.shape[1]
+        assert m <= N, "polynomial has more coefficients than the domain has points"
+        if xfield is None and kind == "x":  # (offset ^ i) * c with a base-field offset, code/univariate.py:169
+            raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
+        if xfield is not None and kind == "b":
+            raise AttributeError("'BaseFieldElement' object has no attribute 'polynomial'")
+        coeffs = eng.download(buf)
+        out = eng.ntt(buf, _ilog2(N), domain.omega.value, offset=domain.offset.value)
+        a = eng.download(out)
+        res = []
+        for c in range(len(columns)):
+            if kind == "b":
+                values = B.np_to_bfe(a[c], domain.offset.field)  # code/fri.py:26-30 via code/univariate.py:169
+                self.remember_planes(values, out[c:c + 1])
+            else:
+                ca = coeffs[3 * c:3 * c + 3]
+                if self._shared_output_period(ca, N):
+                    # sparse interpolants (constant columns) share coefficient objects between outputs in the
+                    # reference's recursion: take the per-column path that models it (see _transform)
+                    values = self.domain_xevaluate(domain, Pn(B.np_to_xfe(ca, first.field)), xfield)
+                else:
+                    values = B.np_to_xfe(a[3 * c:3 * c + 3], xfield)  # scale by lift(offset): offset.field = xfield
+                    self.remember_planes(values, out[3 * c:3 * c + 3])
+            res.append(values)
+        return res
 
     # ------------------------------------------------------------------ code/table.py quotients
     def compile_constraints(self, constraints, n_vars):

@@ -323,3 +323,53 @@ def case_combination(env, glue):
         with pytest.raises(AssertionError):
             glue.combination_codeword(dom, env.xfield, c["max_degree"], rnd, base, args[0], ext, args[1], quo, args[2],
                                       weights[:-1])
+
+
+def seeded_urandom(seed):
+    U = random.Random(seed)
+    return lambda n: bytes(U.getrandbits(8) for _ in range(n))
+
+
+def case_lde(env, glue, make_table=None):
+    """Table.lde / ldex (code/table.py:112-148) against the reference's codewords
+    (tests/golden/lde.json): values and pickles (object graph incl. the shared coefficient objects of constant
+    columns).  `make_table` builds a real reference Table where one is available; otherwise a stub with the
+    attributes the reference's methods read."""
+    g = golden("lde.json")
+    N = g["N"]
+    dom = env.Fri.Domain(env.field(g["offset"]), env.field(g["omega"]), N)
+    for c in g["cases"]:
+        h, bw, fw = c["height"], c["base_width"], c["full_width"]
+        if make_table is not None:
+            t = make_table(env.field, bw, fw, c["length"], c["num_randomizers"], env.field(g["omega"]), N)
+            assert t.height == h and t.omicron.value == c["omicron"]
+        else:
+            t = types.SimpleNamespace(field=env.field, base_width=bw, full_width=fw, length=c["length"], height=h,
+                                      num_randomizers=c["num_randomizers"], omicron=env.field(c["omicron"]))
+        base = [[env.BaseFieldElement(v, env.field) for v in row] for row in c["base"]]
+        ext = [[X(env, *v) for v in row] for row in c["ext"]]
+        draw = seeded_urandom(c["urandom_seed"])
+        t.matrix = [list(row) for row in base]
+        with glue.keep_planes():
+            base_cw = glue.table_lde(t, dom, draw)
+            assert [vals(cw) for cw in base_cw] == c["base_codewords"]
+            assert hashlib.sha256(pickle.dumps(base_cw)).hexdigest() == c["base_pickle_sha256"]
+            if h:
+                assert all(glue.planes_of(cw) is not None for cw in base_cw)
+        t.field = env.xfield
+        t.matrix = [[env.xfield.lift(v) for v in base[r]] + ext[r] for r in range(h)]
+        ext_cw = glue.table_lde(t, dom, draw, xfield=env.xfield)
+        assert [triples(cw) for cw in ext_cw] == c["ext_codewords"]
+        assert hashlib.sha256(pickle.dumps(ext_cw)).hexdigest() == c["ext_pickle_sha256"]
+        # interpolate_columns: the polynomials take the table's values at its points (incl. the drawn randomizers)
+        if h:
+            draw2 = seeded_urandom(5)
+            polys = glue.table_interpolate_columns(t, dom.omega, N, range(bw, fw), draw2)
+            draw3 = seeded_urandom(5)
+            for k, p in enumerate(polys):
+                assert len(p.coefficients) <= h + t.num_randomizers
+                want = [ext[r][k] for r in range(h)] + [env.xfield.sample(draw3(24)) for _ in range(t.num_randomizers)]
+                pts = [t.omicron ^ i for i in range(h)] + [dom.omega ^ (2 * i + 1) for i in range(t.num_randomizers)]
+                assert triples([p.evaluate(env.xfield.lift(x)) for x in pts]) == triples(want)
+    with pytest.raises(AssertionError):  # omega does not have claimed order (code/table.py:113-114)
+        glue.table_interpolate_columns(t, dom.omega, N // 2, range(1), seeded_urandom(1))

@@ -11,7 +11,7 @@ little-endian u64 values; ExtensionFieldElement = c0,c1,c2 with trimmed
 coefficients zero-filled, elements in list order.
 
 Usage:  python tests/golden/make_golden.py <group> [...]
-Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination
+Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination  lde
 Heavy groups are meant to run in the background, one process each.
 """
 import hashlib
@@ -543,6 +543,47 @@ def group_quotients():
     dump("quotients.json", out)
 
 
+def group_lde():
+    """Table.interpolate_columns / lde / ldex (code/table.py:112-148) of the unmodified
+    reference on toy tables (all heights from 0, 0-3 randomizers, constant and zero columns), randomizers drawn
+    from a seeded os.urandom.  Stored: the trace matrices and the resulting codewords."""
+    import table as table_mod
+    from table import Table
+    N = 64
+    dom = Fri.Domain(field.generator(), field.primitive_nth_root(N), N)
+    out = {"N": N, "offset": dom.offset.value, "omega": dom.omega.value, "cases": []}
+    R = random.Random(777)
+    for length, nr, bw, fw in ((0, 1, 2, 3), (1, 1, 2, 4), (2, 0, 1, 2), (3, 1, 3, 5), (8, 2, 2, 4), (13, 3, 3, 6),
+                               (16, 1, 2, 3), (5, 0, 2, 4)):
+        t = Table(field, bw, fw, length, nr, field.primitive_nth_root(N), N)
+        h = t.height
+        base = [[BaseFieldElement(R.randrange(P), field) for _ in range(bw)] for _ in range(h)]
+        for r in range(h):
+            base[r][0] = BaseFieldElement(42, field) if bw > 1 else base[r][0]  # a constant column
+        seed = R.randrange(1 << 30)
+        U = random.Random(seed)
+        table_mod.os.urandom = lambda n: bytes(U.getrandbits(8) for _ in range(n))
+        t.matrix = [list(row) for row in base]
+        base_cw = list(t.lde(dom))  # ldex extends this very list in place (code/table.py:147)
+        ext = [[X(R.randrange(P), R.randrange(P), R.randrange(P)) for _ in range(fw - bw)] for _ in range(h)]
+        for r in range(h):
+            ext[r][0] = X(7, 8, 9)  # constant extension column: shared coefficient objects in the codeword
+            if fw - bw > 1:
+                ext[r][1] = xfield.zero() if r else X(3)
+        t.field = xfield  # what Table.extend does (code/processor_table.py:419)
+        t.matrix = [[xfield.lift(v) for v in base[r]] + ext[r] for r in range(h)]
+        ext_cw = t.ldex(dom, xfield)
+        out["cases"].append({
+            "length": length, "height": h, "num_randomizers": nr, "base_width": bw, "full_width": fw,
+            "omicron": t.omicron.value, "urandom_seed": seed,
+            "base": [[v.value for v in row] for row in base], "ext": [[xfe_triple(v) for v in row] for row in ext],
+            "base_codewords": [[v.value for v in cw] for cw in base_cw],
+            "ext_codewords": [[xfe_triple(v) for v in cw] for cw in ext_cw],
+            "base_pickle_sha256": hashlib.sha256(pickle.dumps(base_cw)).hexdigest(),
+            "ext_pickle_sha256": hashlib.sha256(pickle.dumps(ext_cw)).hexdigest()})
+    dump("lde.json", out)
+
+
 def group_combination():
     """the nonlinear combination block of BrainfuckStark.prove
     (code/brainfuck_stark.py:241-298).  The block is inline, so the reference's OWN statements are cut
@@ -621,6 +662,8 @@ if __name__ == "__main__":
             group_xntt_big()
         elif grp == "bfs":
             group_bfs()
+        elif grp == "lde":
+            group_lde()
         elif grp == "combination":
             group_combination()
         elif grp == "quotients":

@@ -304,3 +304,29 @@ def test_prove_is_recompiled_with_guarded_combination_block(env, monkeypatch):
             pass
     with pytest.raises(LookupError):
         dropin.guarded_prove_source(Moved.prove)
+
+
+def test_table_lde_matches_reference(env):
+    """SURVEY 8(f) row 2 through the reference's own Table class (lde/ldex/interpolate_columns rebound)"""
+    import table
+    fc.case_lde(env, env.glue, make_table=table.Table)
+    # and through the rebound methods themselves, randomizers from the module's os.urandom
+    from util import golden
+    g = golden("lde.json")
+    c = g["cases"][4]
+    dom = env.Fri.Domain(env.field(g["offset"]), env.field(g["omega"]), g["N"])
+    t = table.Table(env.field, c["base_width"], c["full_width"], c["length"], c["num_randomizers"],
+                    env.field(g["omega"]), g["N"])
+    t.matrix = [[env.BaseFieldElement(v, env.field) for v in row] for row in c["base"]]
+    saved = table.os.urandom
+    table.os.urandom = fc.seeded_urandom(c["urandom_seed"])
+    try:
+        cws = t.lde(dom)
+        assert cws is t.codewords and [fc.vals(cw) for cw in cws] == c["base_codewords"]
+        t.field = env.xfield
+        t.matrix = [[env.xfield.lift(v) for v in t.matrix[r]] + [fc.X(env, *v) for v in c["ext"][r]]
+                    for r in range(c["height"])]
+        ext = t.ldex(dom, env.xfield)
+        assert [fc.triples(cw) for cw in ext] == c["ext_codewords"] and len(t.codewords) == c["full_width"]
+    finally:
+        table.os.urandom = saved

@@ -67,3 +67,7 @@ def test_fri_big_transcripts(env, logn):
 
 def test_nonlinear_combination(env, mirror_gpu):
     fc.case_combination(env, mirror_gpu.glue())
+
+
+def test_table_lde(env, mirror_gpu):
+    fc.case_lde(env, mirror_gpu.glue())

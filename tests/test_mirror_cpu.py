@@ -63,3 +63,7 @@ def test_mirror_field_arithmetic(env):
 
 def test_nonlinear_combination(env, mirror_cpu):
     fc.case_combination(env, mirror_cpu.glue())
+
+
+def test_table_lde(env, mirror_cpu):
+    fc.case_lde(env, mirror_cpu.glue())
