@@ -471,11 +471,14 @@ class Glue:
                                               domain.omega.value)
         # code/ntt.py:178-179
         assert not vanishes, "batch inverse does not work when input contains a zero"
+        if self._kept is not None:
+            # Inside keep_planes() (the drop-in's BrainfuckStark.prove): the prover only feeds quotient codewords
+            # to the nonlinear combination, which reads the planes in place -- materialising N Python elements
+            # per constraint would dominate prove().  Elements are built on first access; len / [] / iteration
+            # behave like the reference's list.
+            return [DeviceCodeword(self, out[c], xfield) for c in range(out.shape[0])]
         a = self.engine.download(out.reshape(-1, N)).reshape(-1, 3, N)
-        res = [self.B.np_to_xfe(a[c], xfield) for c in range(a.shape[0])]
-        for c, values in enumerate(res):
-            self.remember_planes(values, out[c])
-        return res
+        return [self.B.np_to_xfe(a[c], xfield) for c in range(a.shape[0])]
 
     # ------------------------------------------------------------------ code/brainfuck_stark.py:241-298
     def combination_codeword(self, domain, xfield, max_degree, randomizer_codeword, base_codewords, base_degree_bounds,

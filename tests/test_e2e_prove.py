@@ -24,3 +24,17 @@ def test_prove_under_dropin_is_byte_identical_and_accepted(tmp_path):
     assert res["reference_verifier_accepts"] is True
     assert res["byte_identical_to_reference_proof"] is True
     assert res["fri_domain_length"] == 1024 and res["engine_calls_launching_kernels"] > 0
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference checkout not available")
+def test_hello_world_prove_is_accepted_by_the_reference_verifier(tmp_path):
+    """BASELINE north star: brainfuck_stark.prove() on the Hello-World trace (907 cycles, FRI domain 2^17) under the
+    drop-in -- about a minute on the host-memory test backend; the all-Python reference needs many hours, so
+    acceptance is the reference's own verifier plus a proof hash that stays fixed under the seeded urandom."""
+    out = str(tmp_path / "res.json")
+    subprocess.check_call([sys.executable, os.path.join(HERE, "e2e_prove_dropin.py"), "fake", out, "hello"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=1800)
+    res = json.load(open(out))
+    assert res["reference_verifier_accepts"] is True
+    assert res["running_time"] == 907 and res["fri_domain_length"] == 1 << 17
+    assert res["proof_sha256"] == "540a9a28053b3195231dc7736163b760d8015a7159b973b85307e45ace4a6f3e"
