@@ -3,7 +3,7 @@ UNMODIFIED reference with the drop-in installed (hot path through the C-ABI surf
 urandom as in SURVEY App. C GV7.  Acceptance = the reference's own verifier accepts, and the
 proof is byte-identical to the all-reference proof recorded in tests/golden/bfs.json.
 
-  python tests/e2e_prove_dropin.py [fake|gpu] [out.json] [program | "hello"]
+  python tests/e2e_prove_dropin.py [fake|gpu] [out.json] [program | "hello"] [input symbols] [golden file]
 
 `fake` runs the engine calls on the host-memory test backend (authoring container, no GPU);
 `gpu` uses libb2s.so on cuda:0 (needs a box that has both a GPU and the reference checkout).
@@ -25,7 +25,7 @@ REFERENCE_DIR = os.environ.get("B2S_REFERENCE_DIR", "/root/reference/code")
 HELLO = ("++++++++[>++++[>++>+++>+++>+<<<<-]>+>+>->>+[<]<-]>>.>---.+++++++..+++.>>.<-.<.+++.------.--------.>>+.>++.")
 
 
-def main(backend="fake", out=None, source="++++"):
+def main(backend="fake", out=None, source="++++", inputs="", golden_name="bfs.json"):
     if source == "hello":
         source = HELLO
     sys.dont_write_bytecode = True
@@ -46,7 +46,7 @@ def main(backend="fake", out=None, source="++++"):
     from vm import VirtualMachine
     from brainfuck_stark import BrainfuckStark
     program = VirtualMachine.compile(source)
-    running_time, input_symbols, output_symbols = VirtualMachine.run(program)
+    running_time, input_symbols, output_symbols = VirtualMachine.run(program, input_data=list(inputs))
     processor_matrix, memory_matrix, instruction_matrix, input_matrix, output_matrix = VirtualMachine.simulate(
         program, input_data=input_symbols)
     bfs = BrainfuckStark(running_time, len(memory_matrix), program, input_symbols, output_symbols)
@@ -59,13 +59,13 @@ def main(backend="fake", out=None, source="++++"):
     t0 = time.time()
     ok = bool(bfs.verify(proof))
     vt = time.time() - t0
-    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "bfs.json")))
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", golden_name)))
     res = {"backend": backend, "program": source, "urandom_seed": 1234, "running_time": running_time,
            "fri_domain_length": bfs.fri.domain.length,
            "proof_len": len(proof), "proof_sha256": hashlib.sha256(proof).hexdigest(),
            "reference_verifier_accepts": ok, "prove_seconds": round(dt, 1), "reference_verify_seconds": round(vt, 1),
            "engine_calls_launching_kernels": int(launches)}
-    if source == "++++":  # the one program the all-reference proof was recorded for
+    if source == golden["program"]:  # programs the all-reference proof was recorded for
         res["byte_identical_to_reference_proof"] = hashlib.sha256(proof).hexdigest() == golden["proof_sha256"]
         res["reference_prove_seconds"] = golden["prove_seconds"]
     if os.environ.get("B2S_DUMP_PROOF"):
@@ -79,4 +79,4 @@ def main(backend="fake", out=None, source="++++"):
 
 
 if __name__ == "__main__":
-    main(*(sys.argv[1:4]))
+    main(*(sys.argv[1:6]))

@@ -456,8 +456,9 @@ def group_xntt_big():
         dump("xntt_big.json", g)
 
 
-def group_bfs():
-    """GV7: BrainfuckStark.prove('++++') with seeded urandom."""
+def group_bfs(source="++++", inputs=(), name="bfs.json"):
+    """GV7: BrainfuckStark.prove('++++') with seeded urandom; `bfs_io`: a program with a
+    loop, input and output symbols (all five tables non-trivial), FRI domain 2048."""
     R = random.Random(1234)
     fake = lambda n: bytes(R.getrandbits(8) for _ in range(n))  # noqa: E731
     os.urandom = fake
@@ -465,8 +466,8 @@ def group_bfs():
     salted_merkle.urandom = fake
     from vm import VirtualMachine
     from brainfuck_stark import BrainfuckStark
-    program = VirtualMachine.compile("++++")
-    running_time, input_symbols, output_symbols = VirtualMachine.run(program)
+    program = VirtualMachine.compile(source)
+    running_time, input_symbols, output_symbols = VirtualMachine.run(program, input_data=list(inputs))
     processor_matrix, memory_matrix, instruction_matrix, input_matrix, output_matrix = VirtualMachine.simulate(
         program, input_data=input_symbols)
     bfs = BrainfuckStark(running_time, len(memory_matrix), program, input_symbols, output_symbols)
@@ -474,7 +475,7 @@ def group_bfs():
     proof = bfs.prove(program, processor_matrix, memory_matrix, instruction_matrix, input_matrix, output_matrix)
     dt = time.time() - t0
     ok = bfs.verify(proof)
-    dump("bfs.json", {"program": "++++", "urandom_seed": 1234, "proof_len": len(proof),
+    dump(name, {"program": source, "inputs": list(inputs), "urandom_seed": 1234, "proof_len": len(proof),
                       "proof_sha256": hashlib.sha256(proof).hexdigest(), "verify": bool(ok),
                       "fri_domain_length": bfs.fri.domain.length, "prove_seconds": round(dt, 1)})
 
@@ -662,6 +663,8 @@ if __name__ == "__main__":
             group_xntt_big()
         elif grp == "bfs":
             group_bfs()
+        elif grp == "bfs_io":
+            group_bfs("++[>,.<-]", ("a", "b"), "bfs_io.json")
         elif grp == "lde":
             group_lde()
         elif grp == "combination":
