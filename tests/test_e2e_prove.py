@@ -38,3 +38,15 @@ def test_hello_world_prove_is_accepted_by_the_reference_verifier(tmp_path):
     assert res["reference_verifier_accepts"] is True
     assert res["running_time"] == 907 and res["fri_domain_length"] == 1 << 17
     assert res["proof_sha256"] == "540a9a28053b3195231dc7736163b760d8015a7159b973b85307e45ace4a6f3e"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference checkout not available")
+def test_prove_with_loop_and_io_is_byte_identical(tmp_path):
+    """a program with a loop, two input and two output symbols (all five tables non-trivial, FRI domain 2048):
+    byte-identical to the all-reference proof in tests/golden/bfs_io.json (reference: 350 s)"""
+    out = str(tmp_path / "res.json")
+    subprocess.check_call([sys.executable, os.path.join(HERE, "e2e_prove_dropin.py"), "fake", out, "++[>,.<-]", "ab",
+                           "bfs_io.json"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    res = json.load(open(out))
+    assert res["reference_verifier_accepts"] is True and res["byte_identical_to_reference_proof"] is True
+    assert res["fri_domain_length"] == 2048
