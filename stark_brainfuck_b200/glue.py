@@ -716,6 +716,20 @@ class Glue:
         codewords, trees = fri.commit(codeword, proof_stream)
         top_level_indices = fri.sample_indices(proof_stream.prover_fiat_shamir(), len(codewords[1]),
                                                len(codewords[-1]), fri.num_colinearity_tests)
+        # every round's indices follow from the top-level ones (code/fri.py:191-197): fetch each tree's leaves
+        # and authentication paths with ONE device call per tree before the query loop pushes them
+        s = fri.num_colinearity_tests
+        idx = [i for i in top_level_indices]
+        wanted = [[] for _ in trees]
+        for i in range(len(trees)):
+            half = len(codewords[i]) // 2
+            idx = [index % half for index in idx]
+            wanted[i] += idx[:s] + [j + half for j in idx[:s]]
+            if i + 1 < len(trees):
+                wanted[i + 1] += idx[:s]
+        for tree, w in zip(trees, wanted):
+            prefetch(tree.leafs, w)
+            prefetch_paths(tree, w)
         indices = [i for i in top_level_indices]
         for i in range(len(trees) - 1):
             indices = [index % (len(codewords[i]) // 2) for index in indices]
@@ -863,6 +877,16 @@ class NodeView:
 
     def open(self, index, depth):
         """code/merkle.py:46-52"""
+        cache = self._cache
+        k = (1 << depth) | index
+        path = []
+        try:  # all siblings already fetched (the usual case after prefetch_paths)
+            while k > 1:
+                path.append(cache[k ^ 1])
+                k >>= 1
+            return path
+        except KeyError:
+            pass
         self.prefetch_paths([index], depth)
         path = []
         k = (1 << depth) | index

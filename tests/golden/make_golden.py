@@ -665,6 +665,8 @@ if __name__ == "__main__":
             group_bfs()
         elif grp == "bfs_io":
             group_bfs("++[>,.<-]", ("a", "b"), "bfs_io.json")
+        elif grp == "bfs_echo":
+            group_bfs("+++++[>,.<-]", tuple("hello"), "bfs_echo.json")
         elif grp == "lde":
             group_lde()
         elif grp == "combination":
