@@ -41,5 +41,38 @@ if what in ("all", "fri"):
     for _ in range(2):
         nodes = eng.merkle_field(cw, tpl)
         nxt, nn = eng.fri_fold(cw, [3, 5, 7], 7, root_of_unity(18), tpl)
+if what in ("all", "next"):  # next-row kernels: quotient codewords and the nonlinear combination at a 2^20 domain
+    import numpy as np
+    rng = np.random.default_rng(3)
+    PM = 18446744069414584321
+    cols = [eng.upload(rng.integers(0, PM, (3, n), dtype=np.uint64))]
+    cols += [eng.upload(rng.integers(0, PM, (1, n), dtype=np.uint64)) for _ in range(31)]
+    cols += [eng.upload(rng.integers(0, PM, (3, n), dtype=np.uint64)) for _ in range(44)]
+    nc = len(cols)
+    wa = rng.integers(0, PM, (nc, 3), dtype=np.uint64)
+    wb = rng.integers(0, PM, (nc, 3), dtype=np.uint64)
+    wb[0] = 0
+    shifts = rng.choice([0, 3, n // 8 - 5, n // 8 + 1, n // 4 - 7, n // 4 - 2, n // 4, n // 16], nc)
+    for _ in range(2):
+        eng.combination(cols, wa, wb, shifts, n, 7, w)
+    del cols
+    # a transition-constraint-like program: 8 constraints x 12 monomials x up to 4 factors over 2 x 12 variables
+    from util import quotient_program
+    import random
+    R = random.Random(5)
+    W = 12
+    program = []
+    for _ in range(8):
+        cons = []
+        for _ in range(12):
+            k = [0] * (2 * W)
+            for _ in range(R.randrange(1, 5)):
+                k[R.randrange(2 * W)] += R.randrange(1, 3)
+            cons.append([k, [R.randrange(PM) for _ in range(3)]])
+        program.append(cons)
+    prog = quotient_program(program)
+    cw = eng.upload(rng.integers(0, PM, (3 * W, n), dtype=np.uint64)).reshape(W, 3, n)
+    for _ in range(2):
+        eng.quotients(cw, n // 1024, *prog, 2, 1024, pow(root_of_unity(10), PM - 2, PM), 7, w)
 torch.cuda.synchronize()
 print("launches", eng.launch_count())

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "common.h"
+#include "glmont.cuh"
 
 namespace {
 
@@ -34,9 +35,19 @@ struct CombSlot {
 struct CombCol {
     const u64 *ptr;
     u64 stride;
-    u64 wa[3], wb[3];
+    u64 wa[3];  // wa * 2^64   (Montgomery form: mont_mul(value, w) is then the plain product)
+    u64 wb[3];  // wb * 2^128  (so that mont_mul(x^shift, wb) is (wb * x^shift) * 2^64)
     u32 planes, pad;
 };
+
+// (wa + wb * x) * 2^64, canonical
+__device__ __forceinline__ xfe comb_weight(const xfe &wa, const xfe &wb, bool shifted, u64 x) {
+    if (!shifted) return wa;
+    xfe w;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) w.c[j] = lcanon(ladd(mont_mul(x, wb.c[j]), wa.c[j]));
+    return w;
+}
 
 template <int K>
 __global__ void __launch_bounds__(256)
@@ -69,18 +80,16 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
                 for (int k = 0; k < K; ++k) v[k] = {{p[k * T], p[stride + k * T], p[2 * stride + k * T]}};
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const xfe w = shifted ? x_add(wa, x_mul_base(wb, x[k])) : wa;
-                    acc[k] = x_add(acc[k], x_mul(w, v[k]));
-                }
+                for (int k = 0; k < K; ++k) x_fma_mont(acc[k], v[k], comb_weight(wa, wb, shifted, x[k]));
             } else {
                 u64 v[K];
 #pragma unroll
                 for (int k = 0; k < K; ++k) v[k] = p[k * T];
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
-                    const xfe w = shifted ? x_add(wa, x_mul_base(wb, x[k])) : wa;
-                    acc[k] = x_add(acc[k], x_mul_base(w, v[k]));
+                    const xfe w = comb_weight(wa, wb, shifted, x[k]);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) acc[k].c[j] = ladd(acc[k].c[j], mont_mul(v[k], w.c[j]));
                 }
             }
         }
@@ -88,9 +97,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         u64 *o = out + t + k * T;
-        o[0] = acc[k].c[0];
-        o[out_stride] = acc[k].c[1];
-        o[2 * out_stride] = acc[k].c[2];
+        o[0] = lcanon(acc[k].c[0]);
+        o[out_stride] = lcanon(acc[k].c[1]);
+        o[2 * out_stride] = lcanon(acc[k].c[2]);
     }
 }
 
@@ -153,8 +162,8 @@ extern "C" int b2s_combination(const uint64_t *const *h_cols, const uint64_t *h_
         C.planes = h_planes[c];
         C.pad = 0;
         for (int j = 0; j < 3; ++j) {
-            C.wa[j] = h_wa[3 * c + j] % GL_P;
-            C.wb[j] = h_wb[3 * c + j] % GL_P;
+            C.wa[j] = gl_to_mont(h_wa[3 * c + j] % GL_P);
+            C.wb[j] = gl_to_mont(gl_to_mont(h_wb[3 * c + j] % GL_P));
         }
     }
     if (n_cols == 0) {

@@ -108,3 +108,26 @@ GL_HD u64 lsub(u64 a, u64 b) {
 
 // the representative in [0, p)
 GL_HD u64 lcanon(u64 x) { return x >= GL_P ? x - GL_P : x; }
+
+// ---- cubic extension with Montgomery multiplications (quotient.cu, combine.cu) ----------------------
+// a * b * 2^-64 in F_p[X]/(X^3 - X + 1): a has lazy coefficients, b canonical ones; lazy result.
+// With b = (value * 2^64) this is the plain product; with a plain b the factor 2^-64 is compensated
+// by the caller (quotient.cu pre-scales each monomial's coefficient by 2^(64 * degree)).
+// X^3 = X - 1, X^4 = X^2 - X  (code/extension_field.py:65-66):
+//   c0 = a0b0 - (a1b2 + a2b1),  c1 = a0b1 + a1b0 + (a1b2 + a2b1) - a2b2,  c2 = a0b2 + a1b1 + a2b0 + a2b2
+GL_HD xfe x_mul_mont(const xfe &a, const xfe &b) {
+    const u64 m12 = mont_mul(a.c[1], b.c[2]), m21 = mont_mul(a.c[2], b.c[1]), m22 = mont_mul(a.c[2], b.c[2]);
+    xfe r;
+    r.c[0] = lsub(lsub(mont_mul(a.c[0], b.c[0]), m12), m21);
+    r.c[1] = lsub(ladd(ladd(ladd(mont_mul(a.c[0], b.c[1]), mont_mul(a.c[1], b.c[0])), m12), m21), m22);
+    r.c[2] = ladd(ladd(ladd(mont_mul(a.c[0], b.c[2]), mont_mul(a.c[1], b.c[1])), mont_mul(a.c[2], b.c[0])), m22);
+    return r;
+}
+// acc (lazy) + a * b * 2^-64, same operand states
+GL_HD void x_fma_mont(xfe &acc, const xfe &a, const xfe &b) {
+    const u64 m12 = mont_mul(a.c[1], b.c[2]), m21 = mont_mul(a.c[2], b.c[1]), m22 = mont_mul(a.c[2], b.c[2]);
+    acc.c[0] = lsub(lsub(ladd(acc.c[0], mont_mul(a.c[0], b.c[0])), m12), m21);
+    acc.c[1] = lsub(ladd(ladd(ladd(ladd(acc.c[1], mont_mul(a.c[0], b.c[1])), mont_mul(a.c[1], b.c[0])), m12), m21), m22);
+    acc.c[2] = ladd(ladd(ladd(ladd(acc.c[2], mont_mul(a.c[0], b.c[2])), mont_mul(a.c[1], b.c[1])), mont_mul(a.c[2], b.c[0])),
+                    m22);
+}

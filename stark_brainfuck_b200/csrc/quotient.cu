@@ -8,19 +8,12 @@
 // one thread evaluates one (constraint, point) pair in extension-field arithmetic; the inverse
 // zerofier is computed once per point by a first kernel.  HBM-bound only in name: a point reads
 // 24 B per variable it uses and writes 24 B, the monomial arithmetic dominates.
+#include <vector>
+
 #include "common.h"
+#include "glmont.cuh"
 
 namespace {
-
-__device__ __forceinline__ xfe x_pow_small(xfe a, u32 e) {
-    xfe acc = {{1, 0, 0}};
-    while (e) {
-        if (e & 1) acc = x_mul(acc, a);
-        e >>= 1;
-        if (e) a = x_mul(a, a);
-    }
-    return acc;
-}
 
 struct ZeroParams {
     u64 w_sq[32];  // omega^(2^b)
@@ -28,7 +21,7 @@ struct ZeroParams {
     u32 kind;
 };
 
-// zinv[i] = inverse zerofier at x_i = offset * omega^i; *flag = 1 if a zerofier vanishes
+// zinv[i] = 2^64 * inverse zerofier at x_i = offset * omega^i; *flag = 1 if a zerofier vanishes
 __global__ void __launch_bounds__(256) zerofier_kernel(const __grid_constant__ ZeroParams Z, u64 N, u64 *zinv, int *flag) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -51,7 +44,7 @@ __global__ void __launch_bounds__(256) zerofier_kernel(const __grid_constant__ Z
         if (z == 0) *flag = 1;
         r = gl_inv(z);
     }
-    zinv[i] = r;
+    zinv[i] = gl_to_mont(r);  // Montgomery form: the final multiplication then needs no extra reduction
 }
 
 __global__ void __launch_bounds__(128)
@@ -63,6 +56,8 @@ __global__ void __launch_bounds__(128)
     if (i >= N) return;
     u64 inext = i + shift;
     if (inext >= N) inext -= N;
+    // Montgomery multiplications by PLAIN codeword values: every factor divides the running product by
+    // 2^64, which the host has compensated by scaling the monomial's coefficient with 2^(64 * degree).
     xfe acc = {{0, 0, 0}};
     for (u32 m = mono_off[c]; m < mono_off[c + 1]; ++m) {
         xfe prod = {{coeffs[3 * m], coeffs[3 * m + 1], coeffs[3 * m + 2]}};
@@ -78,15 +73,16 @@ __global__ void __launch_bounds__(128)
             }
             const u64 *p = cw + (u64)3 * v * N + at;
             const xfe x = {{p[0], p[N], p[2 * N]}};
-            prod = x_mul(prod, x_pow_small(x, e));
+            for (u32 k = 0; k < e; ++k) prod = x_mul_mont(prod, x);
         }
-        acc = x_add(acc, prod);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc.c[j] = ladd(acc.c[j], lcanon(prod.c[j]));
     }
-    const xfe q = x_mul_base(acc, zinv[i]);
+    const u64 zm = zinv[i];
     u64 *o = out + (u64)3 * c * N + i;
-    o[0] = q.c[0];
-    o[N] = q.c[1];
-    o[2 * N] = q.c[2];
+    o[0] = lcanon(mont_mul(acc.c[0], zm));
+    o[N] = lcanon(mont_mul(acc.c[1], zm));
+    o[2 * N] = lcanon(mont_mul(acc.c[2], zm));
 }
 
 }  // namespace
@@ -123,9 +119,17 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
     B2S_CUDA(cudaMallocAsync(&d_zinv, sizeof(u64) * N, st));
     B2S_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
     B2S_CUDA(cudaMemcpyAsync(d_off, h_mono_off, sizeof(u32) * (n_constraints + 1), cudaMemcpyHostToDevice, st));
+    // coefficient * 2^(64 * total degree): see quotient_kernel
+    std::vector<u64> scaled(3 * (size_t)n_mono + 1);
+    for (u32 m = 0; m < n_mono; ++m) {
+        u64 degree = 0;
+        for (u32 f = 0; f < max_factors; ++f) degree += h_factors[m * max_factors + f] & 0xFF;
+        const u64 r = gl_pow(GL_EPS, degree);  // 2^64 = EPS (mod p)
+        for (int j = 0; j < 3; ++j) scaled[3 * m + j] = gl_mul(h_coeffs[3 * m + j] % GL_P, r);
+    }
     if (n_mono) {
         B2S_CUDA(cudaMemcpyAsync(d_fac, h_factors, sizeof(u32) * (size_t)n_mono * max_factors, cudaMemcpyHostToDevice, st));
-        B2S_CUDA(cudaMemcpyAsync(d_coef, h_coeffs, sizeof(u64) * 3 * (size_t)n_mono, cudaMemcpyHostToDevice, st));
+        B2S_CUDA(cudaMemcpyAsync(d_coef, scaled.data(), sizeof(u64) * 3 * (size_t)n_mono, cudaMemcpyHostToDevice, st));
     }
     B2S_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
     ZeroParams Z;
