@@ -665,6 +665,10 @@ if __name__ == "__main__":
             group_bfs()
         elif grp == "bfs_io":
             group_bfs("++[>,.<-]", ("a", "b"), "bfs_io.json")
+        elif grp == "bfs_nested":  # nested loops, FRI domain 8192
+            group_bfs("+++[>+++[>+<-]<-]>>.", (), "bfs_nested.json")
+        elif grp == "bfs_A":  # prints "A": 109 cycles, FRI domain 16384
+            group_bfs("++++++++[>++++++++<-]>+.", (), "bfs_A.json")
         elif grp == "bfs_echo":
             group_bfs("+++++[>,.<-]", tuple("hello"), "bfs_echo.json")
         elif grp == "lde":

@@ -41,12 +41,14 @@ def test_hello_world_prove_is_accepted_by_the_reference_verifier(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference checkout not available")
-def test_prove_with_loop_and_io_is_byte_identical(tmp_path):
-    """a program with a loop, two input and two output symbols (all five tables non-trivial, FRI domain 2048):
-    byte-identical to the all-reference proof in tests/golden/bfs_io.json (reference: 350 s)"""
+@pytest.mark.parametrize("source,inputs,name,domain", [("++[>,.<-]", "ab", "bfs_io.json", 2048),
+                                                       ("+++++[>,.<-]", "hello", "bfs_echo.json", 4096)])
+def test_prove_with_loop_and_io_is_byte_identical(tmp_path, source, inputs, name, domain):
+    """programs with a loop, input and output symbols (all five tables non-trivial, FRI domains 2048 / 4096):
+    byte-identical to the all-reference proofs in tests/golden/bfs_io.json / bfs_echo.json (reference: 350 s / 755 s)"""
     out = str(tmp_path / "res.json")
-    subprocess.check_call([sys.executable, os.path.join(HERE, "e2e_prove_dropin.py"), "fake", out, "++[>,.<-]", "ab",
-                           "bfs_io.json"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+    subprocess.check_call([sys.executable, os.path.join(HERE, "e2e_prove_dropin.py"), "fake", out, source, inputs, name],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
     res = json.load(open(out))
     assert res["reference_verifier_accepts"] is True and res["byte_identical_to_reference_proof"] is True
-    assert res["fri_domain_length"] == 2048
+    assert res["fri_domain_length"] == domain
