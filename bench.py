@@ -273,6 +273,27 @@ def run_b200(args):
             extra["merkle_2p20_hbm_gbs"] = 152.0 * n / (best[0] / 1e3) / 1e9
             extra["fri_commit_2p20_expansion4_ms"] = best[1]
             extra["fri_commit_2p20_hbm_gbs"] = 328.0 * n / (best[1] / 1e3) / 1e9
+            # the whole proof through the reference-named front end (code/fri.py:178-199), codeword already on
+            # the device, host Fiat-Shamir loop and transcript objects included: wall clock
+            from stark_brainfuck_b200.glue import DeviceCodeword, Glue
+            glue = Glue(mirror.binding, eng)
+            old_glue = mirror._glue
+            mirror.set_glue(glue)
+            fri = mirror.fri.Fri(mirror.field.generator(), mirror.field.primitive_nth_root(n), n, 4, 8, mirror.xfield)
+            cwx = eng.ntt(eng.upload(rng.integers(0, P_MOD, size=(3, n // 4), dtype=np.uint64, endpoint=False)), LOG_N, w,
+                          offset=7)
+            best_p = None
+            for _ in range(3):
+                ps = mirror.ip.ProofStream()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                fri.prove(DeviceCodeword(glue, cwx, mirror.xfield), ps)
+                torch.cuda.synchronize(dev)
+                dt = (time.perf_counter() - t0) * 1e3
+                best_p = dt if best_p is None else min(best_p, dt)
+            extra["fri_prove_2p20_expansion4_s8_wall_ms"] = best_p
+            extra["fri_prove_transcript_bytes"] = len(ps.serialize())
+            mirror.set_glue(old_glue)
             mirror.unregister()
     except Exception as e:  # informational only
         extra["fri_error"] = str(e)

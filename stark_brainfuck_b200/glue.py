@@ -361,22 +361,21 @@ class Glue:
                         den = den * (rho[k] - rho[j]) % P
                 dinv = pow(den, P - 2, P)
                 basis.append([c * dinv % P for c in poly])
-            fix = np.zeros((len(cols) * pl, 2 * nr), dtype=np.uint64)  # new values of coefficients [0, nr) and [h, h + nr)
-            low = eng.download(buf[:, :nr])
+            # f = f0 - q + x^h * q touches coefficients [0, nr) and [h, h + nr) (overlapping when h < nr)
+            pos = sorted(set(range(nr)) | set(range(h, h + nr)))
+            where = {p_: i for i, p_ in enumerate(pos)}
+            fix = eng.download(buf[:, pos]).copy()
             for ci in range(len(cols)):
                 at_rho = eng.download(eng.eval_points(f0[ci * pl:(ci + 1) * pl], pts))  # (pl, nr)
                 for s_ in range(pl):
                     t = [(rv[ci][k][s_] - int(at_rho[s_, k])) * zinv[k] % P for k in range(nr)]
                     q = [sum(t[k] * basis[k][i] for k in range(nr)) % P for i in range(nr)]
+                    row = fix[ci * pl + s_]
                     for i in range(nr):
-                        fix[ci * pl + s_, i] = (int(low[ci * pl + s_, i]) - q[i]) % P
-                        fix[ci * pl + s_, nr + i] = q[i]
-            fixd = eng.upload(fix)
-            if h >= nr:
-                buf[:, :nr] = fixd[:, :nr]
-                buf[:, h:] = fixd[:, nr:]
-            else:  # fewer trace points than randomizers: the two ranges overlap, add instead
-                raise NotImplementedError("more randomizers than rows")
+                        row[where[i]] = (int(row[where[i]]) - q[i]) % P
+                    for i in range(nr):
+                        row[where[h + i]] = (int(row[where[h + i]]) + q[i]) % P
+            buf[:, pos] = eng.upload(fix)
         return buf, pl, kind, first
 
     def table_interpolate_columns(self, table, omega, omega_order, column_indices, urandom):

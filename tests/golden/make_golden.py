@@ -555,7 +555,7 @@ def group_lde():
     out = {"N": N, "offset": dom.offset.value, "omega": dom.omega.value, "cases": []}
     R = random.Random(777)
     for length, nr, bw, fw in ((0, 1, 2, 3), (1, 1, 2, 4), (2, 0, 1, 2), (3, 1, 3, 5), (8, 2, 2, 4), (13, 3, 3, 6),
-                               (16, 1, 2, 3), (5, 0, 2, 4)):
+                               (16, 1, 2, 3), (5, 0, 2, 4), (1, 3, 2, 4), (2, 3, 1, 2)):
         t = Table(field, bw, fw, length, nr, field.primitive_nth_root(N), N)
         h = t.height
         base = [[BaseFieldElement(R.randrange(P), field) for _ in range(bw)] for _ in range(h)]
