@@ -370,3 +370,23 @@ def test_combination_golden_and_oracle(eng):
     from stark_brainfuck_b200._lib import B2SError
     with pytest.raises(B2SError):
         eng.combination([eng.upload(rand_bfe(1, 12))], np.zeros((1, 3)), np.zeros((1, 3)), [0], 12, 7, 1)
+
+
+def test_merkle_upper_rebuilds_inner_nodes(eng):
+    """b2s_merkle_upper (the replicated top levels of a multi-GPU tree): inner nodes from the leaf-level digests
+    alone, against the tree b2s_merkle_field built and against the oracle"""
+    import torch
+    tpl = tpl_pair()[0]
+    for logn in (0, 1, 4, 9, 13):
+        n = 1 << logn
+        nodes = eng.merkle_field(eng.upload(rand_xfe(40 + logn, n)), tpl)
+        fresh = torch.zeros_like(nodes)
+        fresh[n:] = nodes[n:]
+        eng.merkle_upper(fresh)
+        assert torch.equal(fresh[1:], nodes[1:])
+        host = np.zeros((2 * n, 64), dtype=np.uint8)
+        host[n:] = np.frombuffer(eng.download_bytes(nodes[n:]), dtype=np.uint8).reshape(n, 64)
+        assert orc.merkle_upper(host)[1:].tobytes() == eng.download_bytes(nodes[1:])
+    from stark_brainfuck_b200._lib import B2SError
+    with pytest.raises(B2SError):
+        eng.merkle_upper(torch.zeros((6, 64), dtype=torch.uint8, device=eng.device))

@@ -38,3 +38,14 @@ def test_sharded_fri_two_gpus():
     assert out.returncode == 0, out.stderr[-2000:]
     rep = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     assert all(c["transcripts_identical"] for c in rep["cases"].values())
+
+
+def test_sharded_fri_code_path_on_one_gpu():
+    """the sharded prover with a one-rank NCCL group (what a single-GPU box can run): golden transcripts"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1", "--master-addr",
+           "127.0.0.1", "--master-port", "29535", os.path.join(HERE, "dist_fri_gpu_check.py"), "--sizes", "8,10,16",
+           "--iters", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rep = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert all(c["transcripts_identical"] and c.get("golden") for c in rep["cases"].values())
