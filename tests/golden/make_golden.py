@@ -11,7 +11,7 @@ little-endian u64 values; ExtensionFieldElement = c0,c1,c2 with trimmed
 coefficients zero-filled, elements in list order.
 
 Usage:  python tests/golden/make_golden.py <group> [...]
-Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination  lde
+Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination  lde  air
 Heavy groups are meant to run in the background, one process each.
 """
 import hashlib
@@ -544,6 +544,37 @@ def group_quotients():
     dump("quotients.json", out)
 
 
+def group_air():
+    """The constraint polynomials of the Brainfuck AIR as data: boundary / transition / terminal
+    `*_constraints_ext` of the reference's five tables (code/processor_table.py:219-357, instruction_table.py,
+    memory_table.py, io_table.py) for seeded challenges and terminals, flattened to (exponent vector,
+    coefficient) lists in dictionary order.  Realistic programs for b2s_quotients: parity against the oracle and
+    the device-time budget of a whole proof (profiles/microbench/prove_device_pipeline.py)."""
+    from vm import VirtualMachine
+    from brainfuck_stark import BrainfuckStark
+    program = VirtualMachine.compile("++[>,.<-]")
+    running_time, input_symbols, output_symbols = VirtualMachine.run(program, input_data=["a", "b"])
+    _, memory_matrix, _, _, _ = VirtualMachine.simulate(program, input_data=input_symbols)
+    bfs = BrainfuckStark(running_time, len(memory_matrix), program, input_symbols, output_symbols)
+    R = random.Random(2718)
+
+    def rx():
+        return X(R.randrange(P), R.randrange(P), R.randrange(P))
+    challenges = [rx() for _ in range(11)]
+    terminals = [rx() for _ in range(5)]
+
+    def flat(constraints):
+        return [[[list(k), xfe_triple(v)] for k, v in c.dictionary.items()] for c in constraints]
+    out = {"challenges": [xfe_triple(c) for c in challenges], "terminals": [xfe_triple(t) for t in terminals],
+           "tables": []}
+    for t in bfs.tables:
+        out["tables"].append({"name": type(t).__name__, "base_width": t.base_width, "full_width": t.full_width,
+                              "boundary": flat(t.boundary_constraints_ext(challenges)),
+                              "transition": flat(t.transition_constraints_ext(challenges)),
+                              "terminal": flat(t.terminal_constraints_ext(challenges, terminals))})
+    dump("air.json", out)
+
+
 def group_lde():
     """Table.interpolate_columns / lde / ldex (code/table.py:112-148) of the unmodified
     reference on toy tables (all heights from 0, 0-3 randomizers, constant and zero columns), randomizers drawn
@@ -671,6 +702,8 @@ if __name__ == "__main__":
             group_bfs("++++++++[>++++++++<-]>+.", (), "bfs_A.json")
         elif grp == "bfs_echo":
             group_bfs("+++++[>,.<-]", tuple("hello"), "bfs_echo.json")
+        elif grp == "air":
+            group_air()
         elif grp == "lde":
             group_lde()
         elif grp == "combination":

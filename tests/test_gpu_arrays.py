@@ -390,3 +390,25 @@ def test_merkle_upper_rebuilds_inner_nodes(eng):
     from stark_brainfuck_b200._lib import B2SError
     with pytest.raises(B2SError):
         eng.merkle_upper(torch.zeros((6, 64), dtype=torch.uint8, device=eng.device))
+
+
+def test_quotients_with_the_brainfuck_air_programs(eng):
+    """the real constraint polynomials of the reference's five tables (tests/golden/air.json: up to 244 monomials,
+    4 factors, exponents to 8 per table) on random codewords: device == oracle, all three zerofier kinds"""
+    from util import quotient_program
+    air = golden("air.json")
+    logn = 10
+    N = 1 << logn
+    w = root_of_unity(logn)
+    for ti, t in enumerate(air["tables"]):
+        W = t["full_width"]
+        cw = np.stack([rand_xfe(3000 + 17 * ti + j, N) for j in range(W)])
+        d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
+        for kind, name in ((1, "boundary"), (2, "transition"), (3, "terminal")):
+            prog = quotient_program(t[name])
+            height = 64
+            oinv = pow(root_of_unity(6), P - 2, P)
+            out, vanishes = eng.quotients(d, N // height, *prog, kind, height, oinv, 7, w)
+            ref, rv = orc.quotients(cw, N // height, *prog, kind, height, oinv, 7, w)
+            assert not vanishes and not rv
+            assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (t["name"], name)
