@@ -84,6 +84,17 @@ def test_uninstall_restores(reference_dropin):
         assert ntt.ntt.__module__ == "ntt" and fri.ntt is ntt.ntt
         assert univariate.Polynomial.scale.__qualname__ == "Polynomial.scale"
         assert fri.Fri.prove.__qualname__ == "Fri.prove"
+        # the next rows too: table methods, salted trees, and the recompiled prove() with its hook
+        import brainfuck_stark
+        import salted_merkle
+        import table
+        assert table.Table.lde.__qualname__ == "Table.lde" and table.Table.ldex.__qualname__ == "Table.ldex"
+        assert table.Table.interpolate_columns.__qualname__ == "Table.interpolate_columns"
+        assert table.Table.transition_quotients.__qualname__ == "Table.transition_quotients"
+        assert salted_merkle.SaltedMerkle.__init__.__qualname__ == "SaltedMerkle.__init__"
+        prove = brainfuck_stark.BrainfuckStark.prove
+        assert prove.__qualname__ == "BrainfuckStark.prove" and not hasattr(prove, "__wrapped__")
+        assert dropin._COMB_HOOK not in brainfuck_stark.__dict__ and dropin._COMB_HOOK not in prove.__code__.co_names
     finally:
         from conftest import REFERENCE_DIR
         dropin.install(REFERENCE_DIR, engine=eng)
