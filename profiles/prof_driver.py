@@ -74,5 +74,33 @@ if what in ("all", "next"):  # next-row kernels: quotient codewords and the nonl
     cw = eng.upload(rng.integers(0, PM, (3 * W, n), dtype=np.uint64)).reshape(W, 3, n)
     for _ in range(2):
         eng.quotients(cw, n // 1024, *prog, 2, 1024, pow(root_of_unity(10), PM - 2, PM), 7, w)
+if what in ("all", "misc"):  # the small kernels: scale, point evaluation, gathers, openings, the multi-GPU exchange step
+    import ctypes as C
+    import numpy as np
+    xs = eng.upload(rand_xfe(3, n))
+    for _ in range(2):
+        eng.scale(x, 7)
+        eng.scale(xs, [3, 5, 7])
+        eng.eval_points(eng.upload(rand_bfe(4, 1 << 16)), eng.upload(rand_bfe(5, 1 << 12)))
+        eng.eval_points(eng.upload(rand_xfe(6, 1 << 16)), eng.upload(rand_bfe(7, 1 << 12)))
+    mirror.register()
+    tpl = mirror.binding.xfe_templates(mirror.xfield)
+    nodes = eng.merkle_field(xs, tpl)
+    idx = list(range(0, n, n // 64))
+    for _ in range(2):
+        eng.gather(xs, idx)
+        eng.merkle_open(nodes, idx)
+    # four-step exchange kernels as rank 0 of 4 sees them (2^20 = 1024 x 1024, 256 local rows), into a local buffer
+    G, n1, n2 = 4, 1024, 1024
+    q, cpp = n1 // G, n2 // G
+    a = torch.randint(0, 2 ** 62, (q, n2), dtype=torch.int64, device=eng.device)
+    send = torch.empty(G * cpp * q, dtype=torch.int64, device=eng.device)
+    ptrs = (C.c_void_p * G)(*[send.data_ptr() + 8 * r * cpp * q for r in range(G)])
+    c = torch.empty((cpp, n1), dtype=torch.int64, device=eng.device)
+    for _ in range(2):
+        eng.check(eng.lib.b2s_dist_twiddle_transpose(C.c_void_p(a.data_ptr()), a.stride(0), q, n2, 0, w, 1, ptrs, G, q, 0,
+                                                     eng.stream_ptr()))
+        eng.check(eng.lib.b2s_block_permute(C.c_void_p(send.data_ptr()), C.c_void_p(c.data_ptr()), G, cpp, q,
+                                            eng.stream_ptr()))
 torch.cuda.synchronize()
 print("launches", eng.launch_count())
