@@ -6,7 +6,7 @@
 
 namespace {
 
-__device__ __forceinline__ xfe x_pow(xfe a, u64 e) {
+GL_HD xfe x_pow(xfe a, u64 e) {
     xfe acc = {{1, 0, 0}};
     while (e) {
         if (e & 1) acc = x_mul(acc, a);
@@ -16,22 +16,38 @@ __device__ __forceinline__ xfe x_pow(xfe a, u64 e) {
     return acc;
 }
 
-// code/univariate.py:168-169: c_i <- factor^i * c_i
+// code/univariate.py:168-169: c_i <- factor^i * c_i.  A thread owns K coefficients i = t + k*T: one power
+// factor^t, then one multiplication by factor^T per step (the reference's `factor ^ i` per coefficient is
+// ~2 log2(i) multiplications each).
+#define SCALE_K 8
 template <int PLANES>
 __global__ void __launch_bounds__(256)
-    scale_kernel(const u64 *__restrict__ in, u64 in_stride, u64 *__restrict__ out, u64 out_stride, u64 n, u64 f0, u64 f1,
-                 u64 f2) {
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    scale_kernel(const u64 *__restrict__ in, u64 in_stride, u64 *__restrict__ out, u64 out_stride, u64 n, u64 T, xfe f,
+                 xfe step) {
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
     if (PLANES == 1) {
-        out[i] = gl_mul(gl_pow(f0, i), in[i]);
+        u64 p = gl_pow(f.c[0], t);
+#pragma unroll
+        for (int k = 0; k < SCALE_K; ++k) {
+            const u64 i = t + k * T;
+            if (i < n) out[i] = gl_mul(p, in[i]);
+            p = gl_mul(p, step.c[0]);
+        }
     } else {
-        const xfe f = x_pow(xfe{{f0, f1, f2}}, i);
-        const xfe c = {{in[i], in[in_stride + i], in[2 * in_stride + i]}};
-        const xfe r = x_mul(f, c);
-        out[i] = r.c[0];
-        out[out_stride + i] = r.c[1];
-        out[2 * out_stride + i] = r.c[2];
+        xfe p = x_pow(f, t);
+#pragma unroll
+        for (int k = 0; k < SCALE_K; ++k) {
+            const u64 i = t + k * T;
+            if (i < n) {
+                const xfe c = {{in[i], in[in_stride + i], in[2 * in_stride + i]}};
+                const xfe r = x_mul(p, c);
+                out[i] = r.c[0];
+                out[out_stride + i] = r.c[1];
+                out[2 * out_stride + i] = r.c[2];
+            }
+            p = x_mul(p, step);
+        }
     }
 }
 
@@ -132,11 +148,14 @@ extern "C" int b2s_scale(const uint64_t *d_in, uint64_t in_stride, uint64_t *d_o
                          uint32_t n_planes, const uint64_t factor[3], void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return 0;
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const u64 T = (n + SCALE_K - 1) / SCALE_K;
+    const unsigned blocks = (unsigned)((T + 255) / 256);
+    const xfe f = {{factor[0] % GL_P, n_planes == 3 ? factor[1] % GL_P : 0, n_planes == 3 ? factor[2] % GL_P : 0}};
+    const xfe step = x_pow(f, T);
     if (n_planes == 1)
-        scale_kernel<1><<<blocks, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, factor[0], 0, 0);
+        scale_kernel<1><<<blocks, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, T, f, step);
     else if (n_planes == 3)
-        scale_kernel<3><<<blocks, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, factor[0], factor[1], factor[2]);
+        scale_kernel<3><<<blocks, 256, 0, st>>>(d_in, in_stride, d_out, out_stride, n, T, f, step);
     else {
         b2s_set_error("scale: n_planes must be 1 or 3");
         return B2S_ERR_ARG;
