@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "common.h"
+#include "glmont.cuh"
 
 namespace {
 
@@ -60,20 +61,26 @@ template <int PP>
 struct EvalAcc;
 template <>
 struct EvalAcc<1> {  // base-field point
-    u64 x;
-    __device__ __forceinline__ void load(const u64 *pts, u64, u64 q) { x = pts[q]; }
-    __device__ __forceinline__ u64 mul(u64 v) const { return gl_mul(v, x); }
-    __device__ __forceinline__ xfe mul(const xfe &v) const { return x_mul_base(v, x); }
+    u64 x, xm;        // the point and its Montgomery form: the Horner steps are mont_mul + lazy add (glmont.cuh)
+    __device__ __forceinline__ void load(const u64 *pts, u64, u64 q) {
+        x = pts[q];
+        xm = gl_to_mont(x);
+    }
+    __device__ __forceinline__ u64 mul(u64 v) const { return mont_mul(v, xm); }
+    __device__ __forceinline__ xfe mul(const xfe &v) const {
+        return {{mont_mul(v.c[0], xm), mont_mul(v.c[1], xm), mont_mul(v.c[2], xm)}};
+    }
     __device__ __forceinline__ u64 times_power(u64 v, u64 e) const { return gl_mul(v, gl_pow(x, e)); }
     __device__ __forceinline__ xfe times_power(const xfe &v, u64 e) const { return x_mul_base(v, gl_pow(x, e)); }
 };
 template <>
 struct EvalAcc<3> {  // extension-field point
-    xfe x;
+    xfe x, xm;
     __device__ __forceinline__ void load(const u64 *pts, u64 pstride, u64 q) {
         x = xfe{{pts[q], pts[pstride + q], pts[2 * pstride + q]}};
+        xm = xfe{{gl_to_mont(x.c[0]), gl_to_mont(x.c[1]), gl_to_mont(x.c[2])}};
     }
-    __device__ __forceinline__ xfe mul(const xfe &v) const { return x_mul(v, x); }
+    __device__ __forceinline__ xfe mul(const xfe &v) const { return x_mul_mont(v, xm); }
     __device__ __forceinline__ xfe times_power(const xfe &v, u64 e) const { return x_mul(v, x_pow(x, e)); }
 };
 
@@ -89,22 +96,22 @@ __global__ void __launch_bounds__(128)
     P.load(pts, pstride, q);
     u64 *dst = partial + (u64)blockIdx.y * 3 * npts + q;
     if constexpr (CP == 1 && PP == 1) {
-        u64 val = 0;
-        for (u64 k = k1; k-- > k0;) val = gl_add(P.mul(val), coeffs[k]);
-        dst[0] = P.times_power(val, k0);
+        u64 val = 0;  // lazy between the steps
+        for (u64 k = k1; k-- > k0;) val = ladd(P.mul(val), coeffs[k]);
+        dst[0] = P.times_power(lcanon(val), k0);
         dst[npts] = 0;
         dst[2 * npts] = 0;
     } else {
         xfe val = {{0, 0, 0}};
         for (u64 k = k1; k-- > k0;) {
             val = P.mul(val);
-            val.c[0] = gl_add(val.c[0], coeffs[k]);
+            val.c[0] = ladd(val.c[0], coeffs[k]);
             if (CP == 3) {
-                val.c[1] = gl_add(val.c[1], coeffs[cstride + k]);
-                val.c[2] = gl_add(val.c[2], coeffs[2 * cstride + k]);
+                val.c[1] = ladd(val.c[1], coeffs[cstride + k]);
+                val.c[2] = ladd(val.c[2], coeffs[2 * cstride + k]);
             }
         }
-        val = P.times_power(val, k0);
+        val = P.times_power(xfe{{lcanon(val.c[0]), lcanon(val.c[1]), lcanon(val.c[2])}}, k0);
         dst[0] = val.c[0];
         dst[npts] = val.c[1];
         dst[2 * npts] = val.c[2];
