@@ -73,9 +73,12 @@ __global__ void __launch_bounds__(256) zerofier_kernel(const __grid_constant__ Z
 #define Q_HOT_MAX 8      // cached powers of a constraint's most-exponentiated variable
 #define Q_THREADS 128
 
-// hot[c] = variable | (max cached exponent << 16) or ~0: the processor table's instruction selectors carry
-// one variable to every power up to 8 in dozens of monomials (code/processor_table.py:130-217), so its powers
-// are built once per thread and reused -- 2.3x fewer extension-field multiplications for that table.
+// hot[c] = variable | (max cached exponent << 16) or ~0.  The processor table's instruction selectors carry
+// one variable to every power up to 8 in dozens of monomials (code/processor_table.py:130-217): 1 000 of the
+// 1 321 extension-field multiplications per point of its transition constraints.  Its powers are built once
+// per thread, and the host has sorted the constraint's monomials by descending exponent of that variable, so
+// the sum is evaluated as a polynomial in it by Horner's rule:
+//     sum_m c_m h^(e_m) rest_m  =  (...((S_8) h + S_7) h + ...) h + S_0,   S_e = sum of c_m rest_m with e_m = e.
 __global__ void __launch_bounds__(Q_THREADS)
     quotient_kernel(const u64 *__restrict__ cw, u64 N, u32 width, u64 shift, const u32 *__restrict__ mono_off,
                     const u64 *__restrict__ coeffs, const u32 *__restrict__ factors, u32 max_factors,
@@ -97,11 +100,15 @@ __global__ void __launch_bounds__(Q_THREADS)
     };
     // Montgomery multiplications by PLAIN codeword values: every factor divides the running product by
     // 2^64, which the host has compensated by scaling the monomial's coefficient with 2^(64 * degree).
-    // Cached powers keep that bookkeeping: c_1 = x, c_(k+1) = c_k * x * 2^-64, so prod * c_e * 2^-64
+    // Cached powers keep that bookkeeping: c_1 = x, c_(k+1) = c_k * x * 2^-64, so acc * c_e * 2^-64
     // equals e successive multiplications by x.
     const u32 hv = hot[c];
     const u32 hvar = hv & 0xFFFF, hmax = hv == 0xFFFFFFFFu ? 0 : hv >> 16;
     u64 *mine = pw + threadIdx.x;
+    auto power = [&](u32 e) {
+        const u64 *q = mine + (e - 1) * 3 * Q_THREADS;
+        return xfe{{q[0], q[Q_THREADS], q[2 * Q_THREADS]}};
+    };
     if (hmax) {
         const xfe x = load(hvar);
         xfe cur = x;
@@ -115,24 +122,32 @@ __global__ void __launch_bounds__(Q_THREADS)
         }
     }
     xfe acc = {{0, 0, 0}};
+    u32 level = 0;  // exponent of the hot variable that acc still has to be multiplied by
     for (u32 m = mono_off[c]; m < mono_off[c + 1]; ++m) {
         xfe prod = {{coeffs[3 * m], coeffs[3 * m + 1], coeffs[3 * m + 2]}};
+        u32 eh = 0;
         for (u32 f = 0; f < max_factors; ++f) {
             const u32 fac = factors[m * max_factors + f];
             const u32 e = fac & 0xFF;
             if (e == 0) continue;
             const u32 v = fac >> 8;
-            if (v == hvar && e <= hmax) {
-                const u64 *q = mine + (e - 1) * 3 * Q_THREADS;
-                prod = x_mul_mont(prod, xfe{{q[0], q[Q_THREADS], q[2 * Q_THREADS]}});
+            if (v == hvar && e <= hmax && eh == 0) {  // (a repeated factor of the same variable stays generic)
+                eh = e;  // applied to the whole group by the Horner step below
             } else {
                 const xfe x = load(v);
                 for (u32 k = 0; k < e; ++k) prod = x_mul_mont(prod, x);
             }
         }
+        if (m == mono_off[c]) {
+            level = eh;
+        } else if (eh < level) {  // monomials arrive by descending eh
+            acc = x_mul_mont(acc, power(level - eh));
+            level = eh;
+        }
 #pragma unroll
         for (int j = 0; j < 3; ++j) acc.c[j] = ladd(acc.c[j], lcanon(prod.c[j]));
     }
+    if (level) acc = x_mul_mont(acc, power(level));
     const u64 zm = zinv[i];
     u64 *o = out + (u64)3 * c * N + i;
     o[0] = lcanon(mont_mul(acc.c[0], zm));
@@ -174,19 +189,7 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
     B2S_CUDA(cudaMallocAsync(&d_zinv, sizeof(u64) * N, st));
     B2S_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
     B2S_CUDA(cudaMemcpyAsync(d_off, h_mono_off, sizeof(u32) * (n_constraints + 1), cudaMemcpyHostToDevice, st));
-    // coefficient * 2^(64 * total degree): see quotient_kernel
-    std::vector<u64> scaled(3 * (size_t)n_mono + 1);
-    for (u32 m = 0; m < n_mono; ++m) {
-        u64 degree = 0;
-        for (u32 f = 0; f < max_factors; ++f) degree += h_factors[m * max_factors + f] & 0xFF;
-        const u64 r = gl_pow(GL_EPS, degree);  // 2^64 = EPS (mod p)
-        for (int j = 0; j < 3; ++j) scaled[3 * m + j] = gl_mul(h_coeffs[3 * m + j] % GL_P, r);
-    }
-    if (n_mono) {
-        B2S_CUDA(cudaMemcpyAsync(d_fac, h_factors, sizeof(u32) * (size_t)n_mono * max_factors, cudaMemcpyHostToDevice, st));
-        B2S_CUDA(cudaMemcpyAsync(d_coef, scaled.data(), sizeof(u64) * 3 * (size_t)n_mono, cudaMemcpyHostToDevice, st));
-    }
-    // per constraint: the variable whose powers are worth caching (most multiplications saved)
+    // per constraint: the variable whose powers are worth caching and factoring out (most multiplications saved) ...
     std::vector<u32> hot(n_constraints, 0xFFFFFFFFu);
     for (u32 c = 0; c < n_constraints; ++c) {
         std::vector<u64> saved(2 * (size_t)width, 0);
@@ -194,15 +197,48 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
         for (u32 m = h_mono_off[c]; m < h_mono_off[c + 1]; ++m)
             for (u32 f = 0; f < max_factors; ++f) {
                 const u32 fac = h_factors[m * max_factors + f], e = fac & 0xFF, v = fac >> 8;
-                if (e >= 2 && e <= Q_HOT_MAX) {
-                    saved[v] += e - 1;
+                if (e >= 1 && e <= Q_HOT_MAX) {
+                    saved[v] += e;  // Horner applies the variable once per exponent level, not per monomial
                     maxe[v] = std::max(maxe[v], e);
                 }
             }
         u32 best = 0;
         for (u32 v = 1; v < 2 * width; ++v)
             if (saved[v] > saved[best]) best = v;
-        if (saved[best] > maxe[best] && 2 * width <= 0xFFFF) hot[c] = best | (maxe[best] << 16);
+        if (maxe[best] >= 2 && saved[best] > 2 * (u64)maxe[best] && 2 * width <= 0xFFFF)
+            hot[c] = best | (maxe[best] << 16);
+    }
+    // ... its monomials sorted by descending exponent of that variable (the kernel's Horner order), and every
+    // coefficient times 2^(64 * total degree) (see quotient_kernel)
+    auto hot_exp = [&](u32 c, u32 m) -> u32 {
+        if (hot[c] == 0xFFFFFFFFu) return 0;
+        const u32 hvar = hot[c] & 0xFFFF, hmax = hot[c] >> 16;
+        for (u32 f = 0; f < max_factors; ++f) {
+            const u32 fac = h_factors[m * max_factors + f], e = fac & 0xFF;
+            if (e && (fac >> 8) == hvar && e <= hmax) return e;
+        }
+        return 0;
+    };
+    std::vector<u32> order(n_mono);
+    for (u32 m = 0; m < n_mono; ++m) order[m] = m;
+    for (u32 c = 0; c < n_constraints; ++c)
+        std::stable_sort(order.begin() + h_mono_off[c], order.begin() + h_mono_off[c + 1],
+                         [&](u32 a, u32 b) { return hot_exp(c, a) > hot_exp(c, b); });
+    std::vector<u64> scaled(3 * (size_t)n_mono + 1);
+    std::vector<u32> facs((size_t)n_mono * mf + 1, 0);
+    for (u32 k = 0; k < n_mono; ++k) {
+        const u32 m = order[k];
+        u64 degree = 0;
+        for (u32 f = 0; f < max_factors; ++f) {
+            facs[(size_t)k * max_factors + f] = h_factors[m * max_factors + f];
+            degree += h_factors[m * max_factors + f] & 0xFF;
+        }
+        const u64 r = gl_pow(GL_EPS, degree);  // 2^64 = EPS (mod p)
+        for (int j = 0; j < 3; ++j) scaled[3 * k + j] = gl_mul(h_coeffs[3 * m + j] % GL_P, r);
+    }
+    if (n_mono) {
+        B2S_CUDA(cudaMemcpyAsync(d_fac, facs.data(), sizeof(u32) * (size_t)n_mono * max_factors, cudaMemcpyHostToDevice, st));
+        B2S_CUDA(cudaMemcpyAsync(d_coef, scaled.data(), sizeof(u64) * 3 * (size_t)n_mono, cudaMemcpyHostToDevice, st));
     }
     B2S_CUDA(cudaMallocAsync(&d_hot, sizeof(u32) * n_constraints, st));
     B2S_CUDA(cudaMemcpyAsync(d_hot, hot.data(), sizeof(u32) * n_constraints, cudaMemcpyHostToDevice, st));
