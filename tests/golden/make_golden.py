@@ -700,6 +700,8 @@ if __name__ == "__main__":
             group_bfs("+++[>+++[>+<-]<-]>>.", (), "bfs_nested.json")
         elif grp == "bfs_A":  # prints "A": 109 cycles, FRI domain 16384
             group_bfs("++++++++[>++++++++<-]>+.", (), "bfs_A.json")
+        elif grp == "bfs_He":  # prints "He": 249 cycles, FRI domain 32768 (about 1.7 h of reference time)
+            group_bfs("++++++++++[>+++++++>++++++++++<<-]>++.>+.", (), "bfs_He.json")
         elif grp == "bfs_echo":
             group_bfs("+++++[>,.<-]", tuple("hello"), "bfs_echo.json")
         elif grp == "air":
