@@ -74,6 +74,13 @@ if what in ("all", "next"):  # next-row kernels: quotient codewords and the nonl
     cw = eng.upload(rng.integers(0, PM, (3 * W, n), dtype=np.uint64)).reshape(W, 3, n)
     for _ in range(2):
         eng.quotients(cw, n // 1024, *prog, 2, 1024, pow(root_of_unity(10), PM - 2, PM), 7, w)
+if what == "frismall":  # the latency-bound tail rounds of a FRI commit: 2^13 .. 2^4 leaves in
+    mirror.register()
+    tpl = mirror.binding.xfe_templates(mirror.xfield)
+    for lg in (13, 10, 8, 7, 5):
+        cw = eng.upload(rand_xfe(2, 1 << lg))
+        for _ in range(2):
+            nxt, nn = eng.fri_fold(cw, [3, 5, 7], 7, root_of_unity(lg), tpl)
 if what in ("all", "misc"):  # the small kernels: scale, point evaluation, gathers, openings, the multi-GPU exchange step
     import ctypes as C
     import numpy as np
