@@ -17,3 +17,13 @@ def test_ntt4_passes_on_host(tmp_path):
     out = subprocess.run([exe, "16"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "0 failed" in out.stdout
+
+
+def test_montgomery_and_lazy_arithmetic_on_host(tmp_path):
+    """glmont.cuh compiled for the host: mont_mul / ladd / lsub / lcanon / x_mul_mont / x_fma_mont and the cached-power
+    bookkeeping of the quotient kernel against plain 128-bit arithmetic (tests/glmont_hostcheck.cpp)"""
+    exe = str(tmp_path / "glmont_hostcheck")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "stark_brainfuck_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "glmont_hostcheck.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "0 failed" in out.stdout, out.stdout + out.stderr
