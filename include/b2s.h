@@ -176,6 +176,16 @@ int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, uint64_t shi
                   uint32_t zerofier_kind, uint64_t height, uint64_t omicron_inv, uint64_t offset, uint64_t omega,
                   uint64_t *d_out, int *h_zero_flag, void *stream);
 
+/* code/fri.py:141-176, the query phase: the codeword elements (`tree.leafs[i]`, :150/:169) and authentication
+ * paths (`tree.open(i)`, code/merkle.py:46-52) of SEVERAL trees in one launch and one synchronisation.  Set s
+ * has h_counts[s] indices (all sets concatenated in h_indices); h_planes[s] / h_nodes[s] are DEVICE addresses,
+ * either may be NULL (then the set contributes zeros to h_values / nothing to h_paths).  h_values: n_planes
+ * values per index; h_paths: log2(h_npo2[s]) * 64 bytes per index of a set with a tree, in index order.
+ * All h_* arrays live in HOST memory. */
+int b2s_open_multi(const uint64_t *const *h_planes, const uint64_t *h_plane_strides, uint32_t n_planes,
+                   const uint8_t *const *h_nodes, const uint64_t *h_npo2, const uint32_t *h_counts,
+                   const uint64_t *h_indices, uint32_t n_sets, uint64_t *h_values, uint8_t *h_paths, void *stream);
+
 /* ---- nonlinear combination codeword --------------------------------
  * code/brainfuck_stark.py:241-298: the reference builds, for every base / extension / quotient
  * codeword c, the terms c and x^shift * c, and sums weight * term over all of them element by

@@ -50,6 +50,7 @@ SIGNATURES = {
     "b2s_gather": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _vp]),
     "b2s_quotients": (_int, [_vp, _u64, _u32, _u64, _u32, _vp, _vp, _vp, _u32, _u32, _u64, _u64, _u64, _u64, _vp,
                              C.POINTER(C.c_int), _vp]),
+    "b2s_open_multi": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
     "b2s_combination": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _u64, _u64, _vp, _u64, _vp]),
     "b2s_dist_twiddle_transpose": (_int, [_vp, _u64, _u32, _u32, _u64, _u64, _u64, C.POINTER(_vp), _u32, _u64, _u64,
                                           _vp]),

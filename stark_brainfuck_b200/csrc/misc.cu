@@ -217,6 +217,83 @@ extern "C" int b2s_eval_points(const uint64_t *d_coeffs, uint64_t coeff_stride, 
     return 0;
 }
 
+// ---- everything the query phase of one FRI proof opens, in one launch and one synchronisation ------------
+namespace {
+struct OpenItem {
+    const u64 *planes;  // or null
+    const u8 *nodes;    // or null
+    u64 stride, npo2, index, path_off;
+    u32 depth, pad;
+};
+
+// one CTA per opened index: thread t < n_planes copies one coefficient, thread t < 4 * depth one 16-byte quarter
+// of the sibling digest at level t / 4 (code/merkle.py:46-52)
+__global__ void __launch_bounds__(128)
+    open_multi_kernel(const OpenItem *__restrict__ items, u32 n_planes, u64 *__restrict__ values, u8 *__restrict__ paths) {
+    const OpenItem it = items[blockIdx.x];
+    const u32 t = threadIdx.x;
+    if (it.planes && t < n_planes) values[(u64)blockIdx.x * n_planes + t] = it.planes[(u64)t * it.stride + it.index];
+    if (it.nodes && t < 4 * it.depth) {
+        const u32 level = t >> 2, quarter = t & 3;
+        const u64 k = ((it.npo2 + it.index) >> level) ^ 1;
+        const uint4 v = *reinterpret_cast<const uint4 *>(it.nodes + k * 64 + quarter * 16);
+        *reinterpret_cast<uint4 *>(paths + it.path_off + (u64)level * 64 + quarter * 16) = v;
+    }
+}
+}  // namespace
+
+extern "C" int b2s_open_multi(const uint64_t *const *h_planes, const uint64_t *h_plane_strides, uint32_t n_planes,
+                              const uint8_t *const *h_nodes, const uint64_t *h_npo2, const uint32_t *h_counts,
+                              const uint64_t *h_indices, uint32_t n_sets, uint64_t *h_values, uint8_t *h_paths,
+                              void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_planes == 0 || n_planes > 128) {
+        b2s_set_error("open_multi: n_planes %u out of range", n_planes);
+        return B2S_ERR_ARG;
+    }
+    std::vector<OpenItem> items;
+    u64 path_bytes = 0, pos = 0;
+    for (u32 s = 0; s < n_sets; ++s) {
+        const u32 depth = h_nodes[s] ? ilog2_u64(h_npo2[s]) : 0;
+        if (h_nodes[s] && (h_npo2[s] == 0 || (h_npo2[s] & (h_npo2[s] - 1)) || depth > 31)) {
+            b2s_set_error("open_multi: tree %u has %llu leaf slots", s, (unsigned long long)h_npo2[s]);
+            return B2S_ERR_ARG;
+        }
+        for (u32 q = 0; q < h_counts[s]; ++q, ++pos) {
+            if (h_nodes[s] && h_indices[pos] >= h_npo2[s]) {
+                b2s_set_error("open_multi: index %llu out of range", (unsigned long long)h_indices[pos]);
+                return B2S_ERR_ARG;
+            }
+            OpenItem it{};
+            it.planes = h_planes[s];
+            it.nodes = h_nodes[s];
+            it.stride = h_plane_strides[s];
+            it.npo2 = h_npo2[s];
+            it.index = h_indices[pos];
+            it.path_off = path_bytes;
+            it.depth = depth;
+            items.push_back(it);
+            path_bytes += (u64)depth * 64;
+        }
+    }
+    if (items.empty()) return 0;
+    const size_t n = items.size(), vbytes = sizeof(u64) * n * n_planes;
+    u8 *d_buf = nullptr;  // [items | values | paths]
+    const size_t ibytes = (sizeof(OpenItem) * n + 15) / 16 * 16, vpad = (vbytes + 15) / 16 * 16;
+    B2S_CUDA(cudaMallocAsync(&d_buf, ibytes + vpad + path_bytes + 16, st));
+    B2S_CUDA(cudaMemcpyAsync(d_buf, items.data(), sizeof(OpenItem) * n, cudaMemcpyHostToDevice, st));
+    B2S_CUDA(cudaMemsetAsync(d_buf + ibytes, 0, vpad, st));  // sets without planes read as zeros
+    open_multi_kernel<<<(unsigned)n, 128, 0, st>>>(reinterpret_cast<const OpenItem *>(d_buf), n_planes,
+                                                   reinterpret_cast<u64 *>(d_buf + ibytes), d_buf + ibytes + vpad);
+    B2S_LAUNCHED();
+    if (h_values) B2S_CUDA(cudaMemcpyAsync(h_values, d_buf + ibytes, vbytes, cudaMemcpyDeviceToHost, st));
+    if (h_paths && path_bytes)
+        B2S_CUDA(cudaMemcpyAsync(h_paths, d_buf + ibytes + vpad, path_bytes, cudaMemcpyDeviceToHost, st));
+    B2S_CUDA(cudaFreeAsync(d_buf, st));
+    B2S_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int b2s_gather(const uint64_t *d_planes, uint64_t plane_stride, uint32_t n_planes,
                           const uint64_t *h_indices, uint32_t n_indices, uint64_t *h_out, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;

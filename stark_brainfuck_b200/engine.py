@@ -161,6 +161,40 @@ class Engine:
                                             out.ctypes.data_as(C.c_void_p), self.stream_ptr()))
         return [[out[q, j].tobytes() for j in range(depth)] for q in range(len(indices))]
 
+    def open_multi(self, sets):
+        """code/fri.py:141-176 in one device call.  sets: [(planes (q, n) or None, nodes (2 npo2, 64) or None, indices)];
+        returns [(values (len, q) uint64 or None, paths (len, depth, 64) uint8 or None)] in the same order."""
+        sets = [(p_, n_, list(i_)) for p_, n_, i_ in sets]
+        ns = len(sets)
+        total = sum(len(i_) for _, _, i_ in sets)
+        if total == 0:
+            return [(None, None)] * ns
+        q = max([p_.shape[0] for p_, _, _ in sets if p_ is not None] + [1])
+        planes = np.array([p_.data_ptr() if p_ is not None else 0 for p_, _, _ in sets], dtype=np.uint64)
+        strides = np.array([(p_.stride(0) if p_.shape[0] > 1 else p_.shape[1]) if p_ is not None else 0
+                            for p_, _, _ in sets], dtype=np.uint64)
+        nodes = np.array([n_.data_ptr() if n_ is not None else 0 for _, n_, _ in sets], dtype=np.uint64)
+        npo2 = np.array([n_.shape[0] // 2 if n_ is not None else 0 for _, n_, _ in sets], dtype=np.uint64)
+        counts = np.array([len(i_) for _, _, i_ in sets], dtype=np.uint32)
+        idx = np.array([i for _, _, i_ in sets for i in i_], dtype=np.uint64)
+        depths = [int(m).bit_length() - 1 if m else 0 for m in npo2]
+        values = np.zeros((total, q), dtype=np.uint64)
+        paths = np.zeros(sum(c * d for c, d in zip(counts.tolist(), depths)) * 64 + 1, dtype=np.uint8)
+        for p_, _, _ in sets:
+            assert p_ is None or (p_.shape[0] == q and (p_.shape[1] == 1 or p_.stride(1) == 1))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        self.check(self.lib.b2s_open_multi(vp(planes), vp(strides), q, vp(nodes), vp(npo2), vp(counts), vp(idx), ns,
+                                           vp(values), vp(paths), self.stream_ptr()))
+        out, vpos, ppos = [], 0, 0
+        for (p_, n_, i_), d in zip(sets, depths):
+            c = len(i_)
+            v = values[vpos:vpos + c] if p_ is not None else None
+            pa = paths[ppos:ppos + c * d * 64].reshape(c, d, 64) if n_ is not None else None
+            vpos += c
+            ppos += c * d * 64 if n_ is not None else 0
+            out.append((v, pa))
+        return out
+
     def root(self, nodes):
         return bytes(self.download_bytes(nodes[1]))
 

@@ -726,9 +726,7 @@ class Glue:
             wanted[i] += idx[:s] + [j + half for j in idx[:s]]
             if i + 1 < len(trees):
                 wanted[i + 1] += idx[:s]
-        for tree, w in zip(trees, wanted):
-            prefetch(tree.leafs, w)
-            prefetch_paths(tree, w)
+        prefetch_openings(self.engine, trees, wanted)
         indices = [i for i in top_level_indices]
         for i in range(len(trees) - 1):
             indices = [index % (len(codewords[i]) // 2) for index in indices]
@@ -736,6 +734,32 @@ class Glue:
         indices = [index % len(codewords[-1]) for index in indices]
         fri.query_last(trees[-1], codewords[-1], indices, proof_stream)
         return top_level_indices
+
+
+def prefetch_openings(engine, trees, wanted):
+    """leaves and authentication paths of several trees with ONE device call (b2s_open_multi): what the query
+    phase of a proof opens.  Trees whose leaves / nodes are not plain device views (host lists, the sharded
+    views of dist_fri) go through their own prefetch."""
+    sets, fills = [], []
+    for tree, w in zip(trees, wanted):
+        leafs, nodes = tree.leafs, getattr(tree, "nodes", None)
+        if type(leafs) is DeviceCodeword:
+            need = leafs.wanted(w)
+            if need:
+                sets.append((leafs._planes, None, need))
+                fills.append(lambda res, leafs=leafs, need=need: leafs.fill(need, res[0]))
+        else:
+            prefetch(leafs, w)
+        if type(nodes) is NodeView:
+            need = nodes.wanted_paths(w, tree.depth)
+            if need:
+                sets.append((None, nodes._dev, need))
+                fills.append(lambda res, nodes=nodes, need=need, depth=tree.depth: nodes.fill_paths(need, res[1], depth))
+        else:
+            prefetch_paths(tree, w)
+    if sets:
+        for fill, res in zip(fills, engine.open_multi(sets)):
+            fill(res)
 
 
 def prefetch(leafs, indices):
@@ -769,17 +793,24 @@ class DeviceCodeword:
     def __len__(self):
         return self._n
 
-    def prefetch(self, indices):
+    def wanted(self, indices):
+        """the indices that still have to be fetched (range-checked like list indexing)"""
         need = [i for i in dict.fromkeys(indices) if i not in self._cache]
-        if not need:
-            return
         for i in need:
             if not 0 <= i < self._n:
                 raise IndexError("list index out of range")
-        vals = self._glue.engine.gather(self._planes, need)
+        return need
+
+    def fill(self, need, vals):
+        """vals: (len(need), 3) uint64 as gathered from the planes"""
         mk, xf = self._glue.B.make_xfe, self._xfield
         for i, v in zip(need, vals.tolist()):
             self._cache[i] = mk(v[0], v[1], v[2], xf)
+
+    def prefetch(self, indices):
+        need = self.wanted(indices)
+        if need:
+            self.fill(need, self._glue.engine.gather(self._planes, need))
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -858,21 +889,28 @@ class NodeView:
         self._fetch_all()
         return (self[k] for k in range(len(self)))
 
-    def prefetch_paths(self, indices, depth):
+    def wanted_paths(self, indices, depth):
+        """the leaf indices whose authentication path is not completely cached yet"""
         if depth == 0:
-            return
+            return []
         need = [i for i in dict.fromkeys(indices)
                 if any((((1 << depth) | i) >> j) ^ 1 not in self._cache for j in range(depth))]
-        need = [i for i in need if 0 <= i < (1 << depth)]
-        if not need:
-            return
-        paths = self._eng.merkle_open(self._dev, need)
+        return [i for i in need if 0 <= i < (1 << depth)]
+
+    def fill_paths(self, need, paths, depth):
+        """paths[q][j]: the 64-byte sibling at level j of leaf need[q] (bytes, or rows of a uint8 array)"""
         for i, path in zip(need, paths):
             k = (1 << depth) | i
             for j in range(depth):
                 sib = (k >> j) ^ 1
                 if sib not in self._cache and not (sib >= self._npo2 + self._n):
-                    self._cache[sib] = path[j]
+                    v = path[j]
+                    self._cache[sib] = v if isinstance(v, bytes) else v.tobytes()
+
+    def prefetch_paths(self, indices, depth):
+        need = self.wanted_paths(indices, depth)
+        if need:
+            self.fill_paths(need, self._eng.merkle_open(self._dev, need), depth)
 
     def open(self, index, depth):
         """code/merkle.py:46-52"""

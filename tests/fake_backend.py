@@ -166,6 +166,34 @@ class FakeLib:
         h_flag._obj.value = int(flag)
         return 0
 
+    def b2s_open_multi(self, h_planes, h_strides, n_planes, h_nodes, h_npo2, h_counts, h_indices, n_sets, h_values,
+                       h_paths, stream):
+        self.launches += 1
+        planes, strides = _u64(_addr(h_planes), n_sets), _u64(_addr(h_strides), n_sets)
+        nodes, npo2 = _u64(_addr(h_nodes), n_sets), _u64(_addr(h_npo2), n_sets)
+        counts = np.ctypeslib.as_array((C.c_uint32 * n_sets).from_address(_addr(h_counts)))
+        total = int(counts.sum())
+        idx = _u64(_addr(h_indices), total)
+        values = _u64(_addr(h_values), total * n_planes).reshape(total, n_planes)
+        pos = ppos = 0
+        for s in range(n_sets):
+            n = int(npo2[s])
+            depth = n.bit_length() - 1 if nodes[s] else 0
+            for q in range(int(counts[s])):
+                i = int(idx[pos])
+                if planes[s]:
+                    for pl in range(n_planes):
+                        values[pos, pl] = _u64(int(planes[s]) + 8 * (int(strides[s]) * pl + i), 1)[0]
+                if nodes[s]:
+                    assert i < n
+                    heap = _u8(int(nodes[s]), 128 * n).reshape(2 * n, 64)
+                    out = _u8(_addr(h_paths) + ppos, depth * 64).reshape(depth, 64) if depth else None
+                    for lvl in range(depth):
+                        out[lvl] = heap[((n + i) >> lvl) ^ 1]
+                    ppos += depth * 64
+                pos += 1
+        return 0
+
     def b2s_combination(self, h_cols, h_strides, h_planes, h_wa, h_wb, h_shifts, n_cols, N, offset, omega, d_out,
                         out_stride, stream):
         self.launches += 1

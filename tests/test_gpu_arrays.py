@@ -412,3 +412,30 @@ def test_quotients_with_the_brainfuck_air_programs(eng):
             ref, rv = orc.quotients(cw, N // height, *prog, kind, height, oinv, 7, w)
             assert not vanishes and not rv
             assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (t["name"], name)
+
+
+def test_open_multi_matches_single_calls(eng):
+    """b2s_open_multi (the whole query phase in one call) against b2s_gather / b2s_merkle_open per tree"""
+    tpl = tpl_pair()[0]
+    R = random.Random(5)
+    trees = []
+    for logn in (12, 7, 3, 1, 0):
+        planes = eng.upload(rand_xfe(70 + logn, 1 << logn))
+        trees.append((planes, eng.merkle_field(planes, tpl), [R.randrange(1 << logn) for _ in range(R.randrange(1, 9))]))
+    sets = []
+    for planes, nodes, idx in trees:
+        sets += [(planes, None, idx), (None, nodes, idx), (planes, nodes, idx[:2])]
+    sets.append((trees[0][0], None, []))
+    got = eng.open_multi(sets)
+    assert len(got) == len(sets)
+    for (planes, nodes, idx), (vals, paths) in zip(sets, got):
+        if planes is not None and idx:
+            assert np.array_equal(vals, eng.gather(planes, idx))
+        else:
+            assert vals is None or len(vals) == 0
+        if nodes is not None and idx:
+            want = eng.merkle_open(nodes, idx)
+            assert [[paths[q, j].tobytes() for j in range(paths.shape[1])] for q in range(len(idx))] == want
+    from stark_brainfuck_b200._lib import B2SError
+    with pytest.raises(B2SError):
+        eng.open_multi([(None, trees[1][1], [1 << 7])])
