@@ -245,6 +245,31 @@ def run_b200(args):
         extra["batched_32_planes_hbm_gbs"] = 16.0 * n * q / (ms_b / 1e3) / 1e9
     except Exception as e:  # informational only
         extra["batched_error"] = str(e)
+    # ---- extra: independent round trips issued round-robin on four streams (what a caller with many single
+    # vectors and no batch to hand over gets: the kernels of different transforms fill each other's idle SMs)
+    try:
+        streams = [torch.cuda.Stream(device=dev) for _ in range(4)]
+        cur = torch.cuda.current_stream(dev)
+        for rep in range(2):  # first repetition warms the per-stream pools
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            start.record()
+            for s_ in streams:
+                s_.wait_event(start)
+            KP = 40
+            for k in range(KP):
+                i = k % NBUF
+                with torch.cuda.stream(streams[k % 4]):
+                    eng.ntt(xs[i], LOG_N, w, out=ys[i])
+                    eng.ntt(ys[i], LOG_N, w, inverse=True, out=zs[i])
+            for s_ in streams:
+                cur.wait_stream(s_)
+            end.record()
+            torch.cuda.synchronize(dev)
+            extra["four_streams_ms_per_round_trip"] = start.elapsed_time(end) / KP
+        assert torch.equal(zs[5], xs[5])
+    except Exception as e:  # informational only
+        extra["four_streams_error"] = str(e)
     # ---- extra: the Merkle / FRI half of the path at a 2^20 domain (BASELINE configs[3] with SURVEY D8's
     # fix), device side: round-0 tree, then fold + next tree per round with fixed challenges ------------
     try:
