@@ -32,7 +32,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .glue import DeviceCodeword, NodeView
+from .glue import DeviceCodeword, NodeView, prefetch_openings
 
 P = 18446744069414584321
 
@@ -352,6 +352,8 @@ class DistFri:
         sharded = [i for i in wanted if isinstance(trees[i].nodes, DistNodeView)]
         self.prefetch_queries([(trees[i].leafs, wanted[i]) for i in sharded] +
                               [(trees[i].nodes, wanted[i]) for i in sharded])
+        # the replicated tail rounds are plain device trees: one local call for all of them
+        prefetch_openings(eng, trees, [wanted.get(i, []) for i in range(len(trees))])
         indices = [i for i in top_level_indices]
         for i in range(len(trees) - 1):
             indices = [index % (len(codewords[i]) // 2) for index in indices]
