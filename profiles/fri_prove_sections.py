@@ -19,6 +19,9 @@ def wrap(obj,name,key):
     setattr(obj,name,w)
 wrap(G,"prefetch","prefetch_leaves"); wrap(G,"prefetch_paths","prefetch_paths")
 wrap(glue,"fri_commit","commit"); wrap(glue,"fri_query","query"); wrap(glue,"fri_query_last","query_last")
+wrap(G.NodeView,"__getitem__","commit:nodes[k] (root download)"); wrap(eng,"fri_fold","commit:fri_fold call")
+wrap(glue,"merkle_build","commit:merkle_build"); wrap(m.ip.ProofStream,"prover_fiat_shamir","fiat_shamir")
+wrap(m.xfield.__class__,"sample","sample")
 for it in range(4):
     T.clear(); ps=m.ip.ProofStream(); torch.cuda.synchronize(); t0=time.perf_counter()
     fri.prove(DeviceCodeword(glue,planes,m.xfield),ps); torch.cuda.synchronize(); tot=time.perf_counter()-t0
