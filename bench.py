@@ -379,10 +379,13 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 500 round trips on the GPU arm -- long enough for a few clock samples; 8 on the CPU reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 8 if args.impl == "reference" else 500
     if args.impl == "reference":
         run_reference(args)
     else:
