@@ -44,11 +44,13 @@ def test_hello_world_prove_is_accepted_by_the_reference_verifier(tmp_path):
 @pytest.mark.parametrize("source,inputs,name,domain", [("++[>,.<-]", "ab", "bfs_io.json", 2048),
                                                        ("+++++[>,.<-]", "hello", "bfs_echo.json", 4096),
                                                        ("+++[>+++[>+<-]<-]>>.", "", "bfs_nested.json", 8192),
-                                                       ("++++++++[>++++++++<-]>+.", "", "bfs_A.json", 16384)])
+                                                       ("++++++++[>++++++++<-]>+.", "", "bfs_A.json", 16384),
+                                                       ("++++++++++[>+++++++>++++++++++<<-]>++.>+.", "", "bfs_He.json",
+                                                        32768)])
 def test_prove_with_loop_and_io_is_byte_identical(tmp_path, source, inputs, name, domain):
-    """programs with a loop, input and output symbols (FRI domains 2048 / 4096 / 8192 / 16384):
-    byte-identical to the all-reference proofs in tests/golden/bfs_io.json / bfs_echo.json / bfs_nested.json / bfs_A.json
-    (reference: 350 s / 755 s / 1569 s / 3045 s)"""
+    """programs with a loop, input and output symbols (FRI domains 2048 ... 32768):
+    byte-identical to the all-reference proofs in tests/golden/bfs_io.json / bfs_echo.json / bfs_nested.json / bfs_A.json / bfs_He.json
+    (reference: 350 s / 755 s / 1569 s / 3045 s / 6109 s)"""
     out = str(tmp_path / "res.json")
     subprocess.check_call([sys.executable, os.path.join(HERE, "e2e_prove_dropin.py"), "fake", out, source, inputs, name],
                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
