@@ -77,13 +77,6 @@ class DistCodeword(DeviceCodeword):
 
     # prefetch = wanted() -> local() -> [sum over ranks] -> fill(); DistFri.prefetch_queries runs the
     # middle step ONCE for all trees and codewords of the query phase
-    def wanted(self, indices):
-        need = [i for i in dict.fromkeys(indices) if i not in self._cache]
-        for i in need:
-            if not 0 <= i < self._n:
-                raise IndexError("list index out of range")
-        return need
-
     def local(self, need):
         """(len(need), 3) uint64: the elements this rank owns, zeros elsewhere"""
         lay, df = self._layout, self._df
@@ -97,13 +90,8 @@ class DistCodeword(DeviceCodeword):
             vals[[pos for pos, _ in items]] = df.eng.gather(self._local[slot], [j for _, j in items])
         return vals
 
-    def fill(self, need, vals):
-        mk, xf = self._glue.B.make_xfe, self._xfield
-        for i, v in zip(need, vals.tolist()):
-            self._cache[i] = mk(v[0], v[1], v[2], xf)
-
     def prefetch(self, indices):
-        need = self.wanted(indices)
+        need = self.wanted(indices)  # wanted() / fill() are the base class's
         if need:
             self.fill(need, self._df.sum_over_ranks(self.local(need)))
 
