@@ -457,6 +457,32 @@ class Glue:
             factors[m, :len(f)] = f
         return (np.asarray(mono_off, dtype=np.uint32), np.asarray(coeffs, dtype=np.uint64).reshape(-1, 3), factors)
 
+    def _table_planes(self, codewords, width, N):
+        """(width, 3, N) device tensor of a table's codewords.  Columns that came out of a device op inside
+        keep_planes() are copied on the device, the others marshalled; inside keep_planes() the assembled tensor
+        is kept for the table's next call (boundary, transition and terminal quotients read the same lists)."""
+        eng = self.engine
+        key = None
+        if self._kept is not None:
+            key = ("table", id(codewords))
+            ent = self._kept.get(key)
+            if ent is not None and ent[0] is codewords and len(ent[2]) == width and \
+                    all(a is b for a, b in zip(ent[2], codewords)):
+                return ent[1]
+        cw = torch.empty((width, 3, N), dtype=torch.int64, device=eng.device)
+        host = [j for j in range(width) if self.planes_of(codewords[j]) is None or
+                self.planes_of(codewords[j]).shape[0] != 3]
+        for j in range(width):
+            if j not in host:
+                cw[j].copy_(self.planes_of(codewords[j]))
+        if host:
+            planes = np.stack([self.B.xfe_to_np(codewords[j]) for j in host])
+            up = eng.upload(planes.reshape(3 * len(host), N)).reshape(len(host), 3, N)
+            cw[torch.tensor(host, device=eng.device)] = up
+        if key is not None:
+            self._kept[key] = (codewords, cw, list(codewords[:width]))
+        return cw
+
     def quotient_codewords(self, domain, codewords, width, constraints, kind, height=0, omicron_inv=1, shift=0):
         """code/table.py:155-178 / :190-236 / :253-286: [mpo.evaluate(point_i) * lift(zerofier_inverse[i])]
         for every constraint over the whole FRI domain, on the device."""
@@ -464,8 +490,7 @@ class Glue:
         n_vars = 2 * width if kind == ZEROFIER_TRANSITION else width
         program = self.compile_constraints(constraints, n_vars)
         xfield = codewords[0][0].field  # acc = point[0].field.zero() (code/multivariate.py:106)
-        planes = np.stack([self.B.xfe_to_np(codewords[j]) for j in range(width)])
-        cw = self.engine.upload(planes.reshape(3 * width, N)).reshape(width, 3, N)
+        cw = self._table_planes(codewords, width, N)
         out, vanishes = self.engine.quotients(cw, shift, *program, kind, height, omicron_inv, domain.offset.value,
                                               domain.omega.value)
         # code/ntt.py:178-179
