@@ -373,3 +373,34 @@ def case_lde(env, glue, make_table=None):
                 assert triples([p.evaluate(env.xfield.lift(x)) for x in pts]) == triples(want)
     with pytest.raises(AssertionError):  # omega does not have claimed order (code/table.py:113-114)
         glue.table_interpolate_columns(t, dom.omega, N // 2, range(1), seeded_urandom(1))
+
+
+def case_quotients_glue(env, glue):
+    """SURVEY 8(f) row 1 through the glue (object lists in, codewords out) against the reference's quotient
+    codewords (tests/golden/quotients.json): plain lists outside keep_planes(), lazy device codewords and the
+    per-table plane cache inside."""
+    from stark_brainfuck_b200.glue import (DeviceCodeword, ZEROFIER_BOUNDARY, ZEROFIER_TERMINAL, ZEROFIER_TRANSITION)
+    g = golden("quotients.json")
+    N, W = g["N"], g["width"]
+    dom = env.Fri.Domain(env.field(g["offset"]), env.field(g["omega"]), N)
+
+    def constraints(program):
+        return [types.SimpleNamespace(dictionary={tuple(k): X(env, *c) for k, c in cons}) for cons in program]
+    for scoped in (False, True):
+        scope = glue.keep_planes() if scoped else None
+        if scope:
+            scope.__enter__()
+        for t in g["tables"]:
+            cws = [[X(env, *v) for v in col] for col in t["codewords"]]
+            if scoped:  # one column as if it had come out of a device op
+                glue.remember_planes(cws[1], glue.engine.upload(np.array(t["codewords"][1], dtype=np.uint64).T.copy()))
+            for kind, name in ((ZEROFIER_BOUNDARY, "boundary"), (ZEROFIER_TRANSITION, "transition"),
+                               (ZEROFIER_TERMINAL, "terminal")):
+                out = glue.quotient_codewords(dom, cws, W, constraints(t[name]["program"]), kind, height=t["height"],
+                                              omicron_inv=t["omicron_inv"],
+                                              shift=t["unit_distance"] if kind == ZEROFIER_TRANSITION else 0)
+                assert all(isinstance(q, DeviceCodeword if scoped else list) for q in out)
+                assert [triples(list(q)) for q in out] == t[name]["out"], name
+        if scope:
+            assert any(isinstance(k, tuple) for k in glue._kept)  # the assembled table planes were kept
+            scope.__exit__(None, None, None)

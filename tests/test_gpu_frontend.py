@@ -71,3 +71,7 @@ def test_nonlinear_combination(env, mirror_gpu):
 
 def test_table_lde(env, mirror_gpu):
     fc.case_lde(env, mirror_gpu.glue())
+
+
+def test_quotients_through_the_glue(env, mirror_gpu):
+    fc.case_quotients_glue(env, mirror_gpu.glue())

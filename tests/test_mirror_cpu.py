@@ -67,3 +67,7 @@ def test_nonlinear_combination(env, mirror_cpu):
 
 def test_table_lde(env, mirror_cpu):
     fc.case_lde(env, mirror_cpu.glue())
+
+
+def test_quotients_through_the_glue(env, mirror_cpu):
+    fc.case_quotients_glue(env, mirror_cpu.glue())
