@@ -44,6 +44,56 @@ def assemble_output(parts, log_n, log_n1):
     return np.ascontiguousarray(d.T).reshape(n1 * n2)
 
 
+def shard_coset_evaluate(engine, coeffs, log_n, omega, offset, rank, world, group=None, gather_coefficients=False):
+    """Coset evaluation / LDE of ONE polynomial over the ranks (code/fri.py:26-37,
+    code/ntt.py:164-168): rank r computes the residue class r of the output,
+        out[G t + r] = sum_j (c_j (offset omega^r)^j) (omega^G)^(j t),      t < n / G,
+    a size-n/G coset transform of the coefficients with offset offset*omega^r and root omega^G -- no exchange.
+    When the polynomial has more than n/G coefficients they are scaled by (offset omega^r)^j and folded modulo
+    n/G first.  coeffs: (1, m) base-field or (3, m) extension-field planes on the device, replicated on every
+    rank -- or, with gather_coefficients=True, this rank's contiguous 1/G of them (one all-gather of the small
+    coefficient vector is then the only collective).  Returns (q, n/G) planes: element t is output G t + r."""
+    G = world
+    assert G & (G - 1) == 0, "power-of-two number of ranks"
+    if gather_coefficients and G > 1:
+        q, m_loc = coeffs.shape
+        full = torch.empty(G * q * m_loc, dtype=coeffs.dtype, device=coeffs.device)
+        dist.all_gather_into_tensor(full, coeffs.contiguous().view(-1), group=group)
+        coeffs = full.view(G, q, m_loc).permute(1, 0, 2).reshape(q, G * m_loc).contiguous()
+    q, m = coeffs.shape
+    assert q in (1, 3)
+    log_g = G.bit_length() - 1
+    n_loc = 1 << (log_n - log_g)
+    w_g = pow(omega, G, P)
+    off_r = offset * pow(omega, rank, P) % P
+    if m <= n_loc:
+        return engine.ntt(coeffs, log_n - log_g, w_g, offset=off_r)
+    # more coefficients than local points: x^(n/G) = (offset omega^r)^(n/G) on this residue class after scaling,
+    # i.e. scale first, then add the chunks of n/G coefficients on top of each other (b2s_combination with unit
+    # weights does the modular sum), then a plain transform
+    chunks = -(-m // n_loc)
+    scaled = engine.scale(coeffs, off_r if q == 1 else [off_r, 0, 0])
+    if chunks * n_loc != m:
+        padded = torch.zeros((q, chunks * n_loc), dtype=scaled.dtype, device=scaled.device)
+        padded[:, :m] = scaled
+        scaled = padded
+    cols = [scaled[:, k * n_loc:(k + 1) * n_loc] for k in range(chunks)]
+    ones = np.zeros((chunks, 3), dtype=np.uint64)
+    ones[:, 0] = 1
+    folded = engine.combination(cols, ones, np.zeros((chunks, 3), dtype=np.uint64), [0] * chunks, n_loc, 1, 1)
+    return engine.ntt(folded[:q], log_n - log_g, w_g)
+
+
+def assemble_residues(parts):
+    """host helper: natural-order output from the per-rank residue classes (q, n/G), rank order"""
+    G = len(parts)
+    q, n_loc = parts[0].shape
+    out = np.empty((q, G * n_loc), dtype=parts[0].dtype)
+    for r, p_ in enumerate(parts):
+        out[:, r::G] = p_
+    return out
+
+
 class DistNTT:
     def __init__(self, engine, group=None, exchange="nccl"):
         self.eng = engine

@@ -66,6 +66,35 @@ def main():
             report[ex] = {"matches_oracle": ok, "roundtrip_exact": ok_rt, "ms_per_transform": float(t[0])}
         except Exception as e:  # report, do not hang the other ranks
             report[ex] = {"error": repr(e)[:300]}
+    # sharded coset evaluation (LDE): every rank one residue class, no exchange
+    try:
+        from stark_brainfuck_b200.dist import assemble_residues, shard_coset_evaluate
+        from util import rand_xfe
+        for name, expansion in (("lde_expansion4", 4), ("lde_expansion1_folded", 1)):
+            c = rand_xfe(9100 + log_n, (1 << log_n) // expansion)
+            cd = eng.upload(c)
+            out = shard_coset_evaluate(eng, cd, log_n, w, 7, rank, world)
+            parts = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(parts, out)
+            ok = None
+            if rank == 0:
+                got = assemble_residues([eng.download(p) for p in parts])
+                ok = bool(np.array_equal(got, orc.coset_evaluate(7, w, c, 1 << log_n)))
+            for _ in range(3):
+                shard_coset_evaluate(eng, cd, log_n, w, 7, rank, world)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.iters):
+                shard_coset_evaluate(eng, cd, log_n, w, 7, rank, world)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / args.iters], device=eng.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            report[name] = {"matches_oracle": ok, "ms_per_evaluation": float(t[0])}
+    except Exception as e:
+        report["lde"] = {"error": repr(e)[:300]}
     if rank == 0:
         print(json.dumps(report))
     dist.destroy_process_group()

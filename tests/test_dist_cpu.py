@@ -116,3 +116,46 @@ def test_sharded_fri_transcript_matches_golden(world, logn, below):
     assert ret[0][5] < 3 * 8 * (1 << logn) // (2 * world)
     if below == 1:
         assert ret[0][5] > 0
+
+
+def _lde_worker(rank, world, port, log_n, expansion, xfe, sharded_coeffs, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_backend import fake_engine
+        from stark_brainfuck_b200.dist import shard_coset_evaluate
+        from util import rand_bfe, rand_xfe, root_of_unity
+        eng = fake_engine()
+        m = (1 << log_n) // expansion
+        c = rand_xfe(9100 + log_n, m) if xfe else rand_bfe(9100 + log_n, m).reshape(1, m)
+        if sharded_coeffs:
+            c = c[:, rank * (m // world):(rank + 1) * (m // world)]
+        out = shard_coset_evaluate(eng, eng.upload(c), log_n, root_of_unity(log_n), 7, rank, world,
+                                   gather_coefficients=sharded_coeffs)
+        ret[rank] = eng.download(out).copy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,log_n,expansion,xfe,sharded_coeffs", [
+    (2, 10, 4, False, False), (4, 10, 4, True, False), (8, 10, 4, False, False), (8, 9, 2, True, False),
+    (4, 8, 1, False, False), (2, 10, 4, True, True), (4, 6, 4, False, True)])
+def test_sharded_coset_evaluate_matches_oracle(world, log_n, expansion, xfe, sharded_coeffs):
+    """every rank evaluates one residue class of the LDE; with more coefficients than local
+    points (expansion < world) they are scaled and folded first"""
+    from oracle import oracle as orc
+    from stark_brainfuck_b200.dist import assemble_residues
+    from util import rand_bfe, rand_xfe, root_of_unity
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() + log_n * 13 + world + 3 * expansion) % 2000
+    mp.spawn(_lde_worker, args=(world, port, log_n, expansion, xfe, sharded_coeffs, ret), nprocs=world, join=True)
+    n = 1 << log_n
+    m = n // expansion
+    c = rand_xfe(9100 + log_n, m) if xfe else rand_bfe(9100 + log_n, m)
+    ref = orc.coset_evaluate(7, root_of_unity(log_n), c, n)
+    got = assemble_residues([ret[r] for r in range(world)])
+    assert np.array_equal(got if xfe else got[0], ref)
