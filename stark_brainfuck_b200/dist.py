@@ -84,6 +84,31 @@ def shard_coset_evaluate(engine, coeffs, log_n, omega, offset, rank, world, grou
     return engine.ntt(folded[:q], log_n - log_g, w_g)
 
 
+def columns_to_rows(planes, group=None):
+    """Column-sharded codewords -> row-sharded ones: every rank holds the SAME number of whole
+    planes (cols_local, N) -- what plane-parallel transforms produce -- and ends up with the index range
+    [r N/G, (r+1) N/G) of ALL planes, (G * cols_local, N/G), plane order = rank order: one all-to-all of
+    8 N cols_local (G-1)/G bytes per rank.  This is the layout zipped-row Merkle leaves and the sharded FRI
+    prover (dist_fri) want."""
+    world = dist.get_world_size(group)
+    c, n = planes.shape
+    assert n % world == 0
+    if world == 1:
+        return planes
+    blk = n // world
+    send = planes.reshape(c, world, blk).permute(1, 0, 2).contiguous()  # [dest rank][plane][index]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    return recv.view(world * c, blk)                                    # [source rank][plane] -> plane-major
+
+
+def shard_eval_points(engine, coeffs, points, rank, world):
+    """code/univariate.py:145-154 on arbitrary points, point-range sharded: every rank
+    evaluates its contiguous share of the points, no collective.  Returns (planes, share of the points)."""
+    share = shard_units(points.shape[1], rank, world)
+    return engine.eval_points(coeffs, points[:, share.start:share.stop].contiguous())
+
+
 def assemble_residues(parts):
     """host helper: natural-order output from the per-rank residue classes (q, n/G), rank order"""
     G = len(parts)

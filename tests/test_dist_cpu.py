@@ -159,3 +159,41 @@ def test_sharded_coset_evaluate_matches_oracle(world, log_n, expansion, xfe, sha
     ref = orc.coset_evaluate(7, root_of_unity(log_n), c, n)
     got = assemble_residues([ret[r] for r in range(world)])
     assert np.array_equal(got if xfe else got[0], ref)
+
+
+def _rows_worker(rank, world, port, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_backend import fake_engine
+        from stark_brainfuck_b200.dist import columns_to_rows, shard_eval_points
+        from util import rand_bfe, rand_xfe
+        eng = fake_engine()
+        n, c = 64, 3
+        mine = np.stack([rand_bfe(500 + rank * c + j, n) for j in range(c)])  # this rank's whole planes
+        rows = columns_to_rows(eng.upload(mine))
+        coeffs, pts = rand_xfe(77, 40), rand_bfe(78, 21).reshape(1, 21)
+        vals = shard_eval_points(eng, eng.upload(coeffs), eng.upload(pts), rank, world)
+        ret[rank] = (eng.download(rows).copy(), eng.download(vals).copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_columns_to_rows_and_sharded_point_evaluation(world):
+    from oracle import oracle as orc
+    from util import rand_bfe, rand_xfe
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_rows_worker, args=(world, 37100 + (os.getpid() * 7 + world) % 1500, ret), nprocs=world, join=True)
+    n, c = 64, 3
+    full = np.stack([rand_bfe(500 + j, n) for j in range(world * c)])  # plane order = rank order
+    for r in range(world):
+        assert np.array_equal(ret[r][0], full[:, r * (n // world):(r + 1) * (n // world)])
+    got = np.concatenate([ret[r][1] for r in range(world)], axis=1)
+    lifted = np.zeros((3, 21), dtype=np.uint64)  # the oracle takes extension-field points for extension coefficients
+    lifted[0] = rand_bfe(78, 21)
+    assert np.array_equal(got, orc.eval_points(rand_xfe(77, 40), lifted))
