@@ -95,6 +95,24 @@ def main():
             report[name] = {"matches_oracle": ok, "ms_per_evaluation": float(t[0])}
     except Exception as e:
         report["lde"] = {"error": repr(e)[:300]}
+    # column-sharded planes -> row-sharded planes (one all-to-all), and point-range sharded evaluation
+    try:
+        from stark_brainfuck_b200.dist import columns_to_rows, shard_eval_points
+        from util import rand_bfe as rb
+        nn, c = 1 << 12, 3
+        mine = np.stack([rb(500 + rank * c + j, nn) for j in range(c)])
+        rows = eng.download(columns_to_rows(eng.upload(mine)))
+        full = np.stack([rb(500 + j, nn) for j in range(world * c)])
+        ok_rows = bool(np.array_equal(rows, full[:, rank * (nn // world):(rank + 1) * (nn // world)]))
+        pts = rb(78, 64).reshape(1, 64)
+        vals = eng.download(shard_eval_points(eng, eng.upload(rb(77, 300)), eng.upload(pts), rank, world))
+        lo = rank * (64 // world)
+        ok_pts = bool(np.array_equal(vals[0], orc.eval_points(rb(77, 300), pts[0])[lo:lo + 64 // world]))
+        flag = torch.tensor([1 if ok_rows and ok_pts else 0], device=eng.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        report["columns_to_rows_and_point_shards_ok"] = bool(flag.item())
+    except Exception as e:
+        report["columns_to_rows_and_point_shards_ok"] = repr(e)[:300]
     if rank == 0:
         print(json.dumps(report))
     dist.destroy_process_group()

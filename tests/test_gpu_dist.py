@@ -25,6 +25,7 @@ def test_sharded_ntt_two_gpus():
     if "error" not in rep.get("p2p", {"error": 1}):
         assert rep["p2p"]["matches_oracle"] is True and rep["p2p"]["roundtrip_exact"] is True
     assert rep["lde_expansion4"]["matches_oracle"] is True and rep["lde_expansion1_folded"]["matches_oracle"] is True
+    assert rep["columns_to_rows_and_point_shards_ok"] is True
 
 
 def test_sharded_fri_two_gpus():
