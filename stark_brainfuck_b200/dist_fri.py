@@ -46,6 +46,25 @@ def scatter_pair_blocks(planes, rank, world):
     return (np.ascontiguousarray(a[:, lo:lo + blk]), np.ascontiguousarray(a[:, n // 2 + lo:n // 2 + lo + blk]))
 
 
+def residues_to_pair_blocks(planes, group=None):
+    """The residue-class shard of a codeword that dist.shard_coset_evaluate produces (rank r: c[G t + r], (q, N/G))
+    -> the pair of blocks DistFri.prove starts from (A_r, B_r, each (q, N/2G)): one all-to-all of the codeword
+    ("the LDE row's output is residue-sharded; the FRI row wants index ranges").  Needs N >= 2 G^2."""
+    world = dist.get_world_size(group)
+    q, n_loc = planes.shape
+    if world == 1:
+        return planes[:, :n_loc // 2].contiguous(), planes[:, n_loc // 2:].contiguous()
+    blk = n_loc // 2            # = N / 2G, the block length
+    assert blk % world == 0, "codeword too short for this many ranks"
+    u = blk // world
+    # t = h * (N/2G) + d * (B/G) + u'  <->  index h * N/2 + d * B + (G u' + r): block d of half h, offset G u' + r
+    send = planes.reshape(q, 2, world, u).permute(2, 0, 1, 3).contiguous()  # [destination d][plane][half][u']
+    recv = torch.empty_like(send)                                           # [source r][plane][half][u']
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    blocks = recv.permute(1, 2, 3, 0).reshape(q, 2, blk)                    # offset G u' + r
+    return blocks[:, 0].contiguous(), blocks[:, 1].contiguous()
+
+
 class _Layout:
     """where the leaves of one round live: subtree s covers leaves [s*blk, (s+1)*blk) and is slot
     `slot` of rank `rank`, (rank, slot) = owner(s)"""

@@ -71,6 +71,18 @@ def main():
                 np.random.default_rng(logn).integers(0, 18446744069414584321, (3, n // expansion), dtype=np.uint64)
             full = eng.ntt(eng.upload(coeffs), logn, root_of_unity(logn), offset=7)  # code/fri.py:33-39 on the device
             fri = env.Fri(env.field.generator(), env.field.primitive_nth_root(n), n, expansion, s, env.xfield)
+            # the same blocks through the sharded chain: residue-class LDE (no exchange) + one all-to-all
+            from stark_brainfuck_b200.dist import shard_coset_evaluate
+            from stark_brainfuck_b200.dist_fri import residues_to_pair_blocks
+            if n >= 2 * world * world:
+                res = shard_coset_evaluate(eng, eng.upload(coeffs), logn, root_of_unity(logn), 7, rank, world)
+                ca, cb = residues_to_pair_blocks(res)
+                blk = n // (2 * world)
+                same = torch.equal(ca, full[:, rank * blk:(rank + 1) * blk]) and \
+                    torch.equal(cb, full[:, n // 2 + rank * blk:n // 2 + (rank + 1) * blk])
+                chain_ok = torch.tensor([1 if same else 0], device="cuda")
+                dist.all_reduce(chain_ok, op=dist.ReduceOp.MIN)
+                report.setdefault("chain_blocks_identical", {})[str(logn)] = bool(chain_ok.item())
             shard, one = DistFri(glue), DistFri(glue, group=solo)
             best = {"sharded_ms": 1e30, "one_gpu_ms": 1e30}
             for _ in range(args.iters):
@@ -98,6 +110,7 @@ def main():
         print(json.dumps(report))
     dist.destroy_process_group()
     bad = [k for k, v in report["cases"].items() if not v["transcripts_identical"]]
+    bad += [k for k, v in report.get("chain_blocks_identical", {}).items() if not v]
     sys.exit(1 if bad else 0)
 
 

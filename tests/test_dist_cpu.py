@@ -197,3 +197,50 @@ def test_columns_to_rows_and_sharded_point_evaluation(world):
     lifted = np.zeros((3, 21), dtype=np.uint64)  # the oracle takes extension-field points for extension coefficients
     lifted[0] = rand_bfe(78, 21)
     assert np.array_equal(got, orc.eval_points(rand_xfe(77, 40), lifted))
+
+
+def _lde_fri_worker(rank, world, port, logn, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import frontend_cases as fc
+        from fake_backend import fake_engine
+        from stark_brainfuck_b200 import mirror
+        from stark_brainfuck_b200.dist import shard_coset_evaluate
+        from stark_brainfuck_b200.dist_fri import DistFri, residues_to_pair_blocks
+        from stark_brainfuck_b200.glue import Glue
+        from util import rand_xfe, root_of_unity
+        mirror.register()
+        glue = Glue(mirror.binding, fake_engine())
+        mirror.set_glue(glue)
+        m = mirror
+        env = fc.make_env(m.algebra, m.univariate, m.extension_field, m.ntt, m.merkle, m.ip, m.fri)
+        n = 1 << logn
+        fri = env.Fri(env.field.generator(), env.field.primitive_nth_root(n), n, 4, 8, env.xfield)
+        coeffs = rand_xfe(200 + logn, n // 4)  # the polynomial behind tests/golden/fri_small.json
+        shard = shard_coset_evaluate(glue.engine, glue.engine.upload(coeffs), logn, root_of_unity(logn), 7, rank, world)
+        a, b = residues_to_pair_blocks(shard)
+        ps = env.ProofStream()
+        top = DistFri(glue).prove(fri, a, b, ps, env.Merkle, replicate_below=4)
+        ret[rank] = (top, ps.serialize())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,logn", [(2, 8), (4, 10)])
+def test_sharded_lde_feeds_sharded_fri(world, logn):
+    """polynomial -> sharded coset evaluation (no exchange) -> one all-to-all into pair blocks -> sharded FRI proof:
+    the transcript is the golden one the reference produced from the same polynomial"""
+    import hashlib
+    from util import golden
+    e = golden("fri_small.json")["gv6"][str(logn)]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_lde_fri_worker, args=(world, 38300 + (os.getpid() * 3 + world + logn) % 1500, logn, ret), nprocs=world,
+             join=True)
+    for r in range(world):
+        top, ser = ret[r]
+        assert top == e["top_level_indices"] and hashlib.sha256(ser).hexdigest() == e["transcript_sha256"]
