@@ -125,6 +125,25 @@ int b2s_merkle_field(const uint64_t *d_planes, uint64_t plane_stride, uint64_t n
  * (code/merkle.py:26).  d_nodes holds 2*npo2 slots. */
 int b2s_merkle_blobs(const uint8_t *d_bytes, const uint64_t *d_offsets, uint64_t n_leafs, uint64_t npo2,
                      uint8_t *d_nodes, void *stream);
+/* Leaves that are ROWS of several codewords -- the zipped, salted leaves of BrainfuckStark.prove
+ * (code/brainfuck_stark.py:178-180, :197-199; code/salted_merkle.py:25-35):
+ *     slot n+r = blake2b(pickle.dumps(row_r) | pickle.dumps(salt_r)),   row_r = (cw_0[r], cw_1[r], ...).
+ * The glue derives ONE byte template per tree from a sample row of the caller's own objects (the elements of
+ * a row carry different `field` objects, so memo indices are per tree); the device splices the integers:
+ *     PROTO 4 | FRAME(len) | seg_0 INT(v_0) seg_1 ... INT(v_{S-1}) seg_S | salt_prefix salt_r salt_suffix
+ * seg_j = h_tpl[h_seg_off[j] .. h_seg_off[j+1]) (n_slots + 2 offsets).  h_planes: HOST array of n_planes DEVICE
+ * pointers (n values each), in row order; h_modes[p]: 0 = integer slot, 1 = integer slot that must be non-zero
+ * (top coefficient of an extension-field element), 2 = no slot, value must be zero (a trimmed coefficient,
+ * code/extension_field.py:6-9).  A row that violates its modes has a different pickle shape: it is NOT hashed
+ * and its index is returned in h_exceptions (capacity = number of rows processed); the caller hashes those rows
+ * with the template of their shape through d_rows (DEVICE list of n_rows row indices; NULL = all n rows).
+ * d_salts: n * salt_len bytes (NULL: unsalted rows).  build_upper != 0 and no exceptions: the inner nodes
+ * (code/salted_merkle.py:38-44) are built in the same call.  n must be a power of two.  Synchronises. */
+int b2s_merkle_rows(const uint64_t *const *h_planes, const uint8_t *h_modes, uint32_t n_planes, uint64_t n,
+                    const uint8_t *h_tpl, const uint32_t *h_seg_off, uint32_t n_slots, const uint8_t *d_salts,
+                    uint32_t salt_len, const uint8_t *h_salt_prefix, uint32_t salt_prefix_len,
+                    const uint8_t *h_salt_suffix, uint32_t salt_suffix_len, const uint32_t *d_rows, uint64_t n_rows,
+                    uint8_t *d_nodes, int build_upper, uint32_t *h_exceptions, uint32_t *h_n_exceptions, void *stream);
 /* code/merkle.py:35-41 alone: the inner nodes above `npo2` digests that the caller has placed in
  * slots [npo2, 2*npo2) of d_nodes (multi-GPU trees: the top levels over the subtree roots that the
  * ranks exchanged). */

@@ -564,6 +564,63 @@ int orc_merkle_blobs(const u8 *bytes, const u64 *offsets, u64 n, u64 npo2, u8 *n
     return 0;
 }
 
+/* code/salted_merkle.py:25-35 over rows of codewords (code/brainfuck_stark.py:178-180, :197-199):
+ * leaf r = blake2b(pickle.dumps(row_r) | pickle.dumps(salt_r)).  The row pickle is the byte template of the
+ * caller's tuple with one integer per emitted plane (mode 0/1; mode 2 = a trimmed coefficient, must be zero,
+ * code/extension_field.py:6-9).  Rows whose shape differs from the template are listed in `exceptions` and
+ * left unhashed.  rows == NULL: all n rows.  Returns the number of exceptions, or -1 on bad arguments. */
+long orc_row_leaves(const u64 *const *planes, const u8 *modes, u32 n_planes, u64 n, const u8 *tpl, const u32 *seg_off,
+                    u32 n_slots, const u8 *salts, u32 salt_len, const u8 *salt_pre, u32 salt_pre_len,
+                    const u8 *salt_suf, u32 salt_suf_len, const u32 *rows, u64 n_rows, u8 *nodes, u32 *exceptions) {
+    if (n == 0 || (n & (n - 1))) return -1;
+    const u64 count = rows ? n_rows : n;
+    const u32 tpl_len = seg_off[n_slots + 1];
+    u8 *msg = (u8 *)malloc(11 + tpl_len + 11 * (size_t)n_planes + salt_pre_len + salt_len + salt_suf_len + 16);
+    long n_exc = 0;
+    for (u64 t = 0; t < count; ++t) {
+        const u64 r = rows ? rows[t] : t;
+        int ok = 1;
+        for (u32 p = 0; p < n_planes; ++p) {
+            const u64 v = planes[p][r];
+            if (modes[p] == 2 ? v != 0 : (modes[p] == 1 && v == 0)) ok = 0;
+        }
+        if (!ok) {
+            exceptions[n_exc++] = (u32)r;
+            continue;
+        }
+        u32 len = 11, slot = 0;
+        for (u32 p = 0; p < n_planes; ++p) {
+            if (modes[p] == 2) continue;
+            memcpy(msg + len, tpl + seg_off[slot], seg_off[slot + 1] - seg_off[slot]);
+            len += seg_off[slot + 1] - seg_off[slot];
+            len += orc_pickle_uint(planes[p][r], msg + len);
+            ++slot;
+        }
+        if (slot != n_slots) {
+            free(msg);
+            return -1;
+        }
+        memcpy(msg + len, tpl + seg_off[slot], seg_off[slot + 1] - seg_off[slot]);
+        len += seg_off[slot + 1] - seg_off[slot];
+        const u64 body = len - 11;
+        msg[0] = 0x80;
+        msg[1] = 0x04;
+        msg[2] = 0x95;
+        for (int i = 0; i < 8; ++i) msg[3 + i] = (u8)(body >> (8 * i));
+        if (salts) {
+            memcpy(msg + len, salt_pre, salt_pre_len);
+            len += salt_pre_len;
+            memcpy(msg + len, salts + r * salt_len, salt_len);
+            len += salt_len;
+            memcpy(msg + len, salt_suf, salt_suf_len);
+            len += salt_suf_len;
+        }
+        orc_blake2b(msg, len, nodes + 64 * (n + r));
+    }
+    free(msg);
+    return n_exc;
+}
+
 /* code/merkle.py:46-52: sibling digests from the leaf level upward */
 void orc_merkle_open(const u8 *nodes, u64 npo2, u64 index, u8 *path /* depth*64 */) {
     u64 k = npo2 | index;

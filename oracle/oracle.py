@@ -338,3 +338,25 @@ def merkle_open(nodes, index):
     path = np.zeros((max(depth, 1), 64), dtype=np.uint8)
     lib().orc_merkle_open(_p(nodes), npo2, index, _p(path))
     return [bytes(path[j]) for j in range(depth)]
+
+
+def row_leaves(planes, modes, tpl, seg_off, n, nodes, salts=None, salt_pre=b"", salt_suf=b"", rows=None):
+    """digests of zipped-row leaves (code/salted_merkle.py:25-35) into slots [n, 2n) of `nodes`
+    ((2n, 64) uint8, modified in place).  planes: list of (n,) uint64 arrays.  Returns the exception rows."""
+    planes = [np.ascontiguousarray(a, dtype=np.uint64) for a in planes]
+    ptrs = (C.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
+    modes = np.ascontiguousarray(modes, dtype=np.uint8)
+    seg = np.ascontiguousarray(seg_off, dtype=np.uint32)
+    n_slots = len(seg) - 2
+    exc = np.zeros(n + 1, dtype=np.uint32)
+    rws = None if rows is None else np.ascontiguousarray(rows, dtype=np.uint32)
+    sl = None if salts is None else np.ascontiguousarray(salts, dtype=np.uint8)
+    f = lib().orc_row_leaves
+    f.restype = C.c_long
+    got = f(ptrs, _p(modes), len(planes), C.c_uint64(n), bytes(tpl), _p(seg), n_slots,
+            _p(sl) if sl is not None else None, sl.shape[1] if sl is not None else 0, bytes(salt_pre), len(salt_pre),
+            bytes(salt_suf), len(salt_suf), _p(rws) if rws is not None else None,
+            C.c_uint64(len(rws) if rws is not None else 0), _p(nodes), _p(exc))
+    if got < 0:
+        raise ValueError("orc_row_leaves: bad arguments")
+    return exc[:got].copy()

@@ -44,6 +44,8 @@ SIGNATURES = {
     "b2s_eval_points": (_int, [_vp, _u64, _u32, _u64, _vp, _u64, _u32, _u64, _vp, _u64, _vp]),
     "b2s_merkle_field": (_int, [_vp, _u64, _u64, _TP, _vp, _vp]),
     "b2s_merkle_blobs": (_int, [_vp, _vp, _u64, _u64, _vp, _vp]),
+    "b2s_merkle_rows": (_int, [_vp, _vp, _u32, _u64, _vp, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u32, _vp, _u64, _vp,
+                               _int, _vp, _vp, _vp]),
     "b2s_merkle_upper": (_int, [_vp, _u64, _vp]),
     "b2s_merkle_open": (_int, [_vp, _u64, _vp, _u32, _vp, _vp]),
     "b2s_fri_fold": (_int, [_vp, _u64, _u64, C.POINTER(_u64), _u64, _u64, _vp, _u64, _TP, _vp, _vp]),

@@ -10,7 +10,7 @@
 //                     rows land directly at C_r[k2_local][g*q + j1_local], so the transfer is part
 //                     of the compute kernel and overlaps it tile by tile.
 #include "common.h"
-#include "glfast.cuh"
+#include "glmont.cuh"
 
 namespace {
 
@@ -38,17 +38,18 @@ __global__ void __launch_bounds__(256) dist_twiddle_transpose_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const u64 j1 = P.row_base + r0 + ty + 8 * i;
-        tw[i] = fpow_sq(P.w_sq, P.tw_mul * j1 * (u64)tx);
-        ratio[i] = fpow_sq(P.w_sq, P.tw_mul * j1 * 32);
+        // both in Montgomery form: mont_mul(x, tw) = x * omega^e, mont_mul(tw, ratio) steps tw by 32 columns
+        tw[i] = gl_to_mont(gl_pow_sq(P.w_sq, P.tw_mul * j1 * (u64)tx));
+        ratio[i] = gl_to_mont(gl_pow_sq(P.w_sq, P.tw_mul * j1 * 32));
     }
     for (u32 c0 = 0; c0 < P.cols; c0 += 32) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const u32 r = r0 + ty + 8 * i, c = c0 + tx;
             u64 v = 0;
-            if (r < P.rows && c < P.cols) v = canon(fmul(P.in[(u64)r * P.in_stride + c], tw[i]));
+            if (r < P.rows && c < P.cols) v = lcanon(mont_mul(P.in[(u64)r * P.in_stride + c], tw[i]));
             tile[ty + 8 * i][tx] = v;
-            tw[i] = fmul(tw[i], ratio[i]);
+            tw[i] = mont_mul(tw[i], ratio[i]);
         }
         __syncthreads();
 #pragma unroll

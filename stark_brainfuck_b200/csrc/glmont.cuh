@@ -1,4 +1,5 @@
-// glmont.cuh -- Goldilocks arithmetic for the register-blocked NTT passes (ntt3.cuh).
+// glmont.cuh -- Goldilocks arithmetic with Montgomery-form multipliers (NTT passes of ntt4.cuh, quotient.cu,
+// combine.cu, misc.cu, dist.cu).
 //
 // Values are u64 residues mod p = 2^64 - 2^32 + 1 in one of two states:
 //   "lazy"       any u64 (stands for its residue)
@@ -11,7 +12,7 @@
 // whose canonical result lets the butterfly's add/sub run without a separate reduction:
 //   ladd(a, b): a lazy, b canonical -> lazy      lsub(a, b): a lazy, b canonical -> lazy
 // The functions compile for the host as well (plain C) so that the pass logic can be checked
-// on a machine without a GPU (tests/ntt3_hostcheck.cu).
+// on a machine without a GPU (tests/ntt4_hostcheck.cpp, tests/glmont_hostcheck.cpp).
 #pragma once
 #include "gl64.cuh"
 

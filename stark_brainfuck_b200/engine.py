@@ -144,6 +144,35 @@ class Engine:
         self.check(self.lib.b2s_merkle_blobs(_ptr(d_data), _ptr(d_offs), n, npo2, _ptr(nodes), self.stream_ptr()))
         return nodes
 
+    def merkle_rows(self, planes, modes, tpl, seg_off, n, salts=None, salt_pre=b"", salt_suf=b"", rows=None,
+                    nodes=None, build_upper=True):
+        """code/salted_merkle.py:25-35 over rows of codewords.  planes: list of (n,) device int64 views in row order;
+        modes / tpl / seg_off: the row template (marshal.RowTemplate); salts: (n, salt_len) uint8 device tensor.
+        rows: optional device int32 tensor of row indices.  Returns (nodes (2n, 64) uint8, exception rows)."""
+        for t in planes:
+            assert t.dtype == torch.int64 and t.shape == (n,) and t.stride(0) == 1
+        ptrs = np.array([t.data_ptr() for t in planes], dtype=np.uint64)
+        modes = np.ascontiguousarray(modes, dtype=np.uint8)
+        seg = np.ascontiguousarray(seg_off, dtype=np.uint32)
+        tpl = np.frombuffer(bytes(tpl) + b"\0", dtype=np.uint8)
+        pre = np.frombuffer(bytes(salt_pre) + b"\0", dtype=np.uint8)
+        suf = np.frombuffer(bytes(salt_suf) + b"\0", dtype=np.uint8)
+        if nodes is None:
+            nodes = torch.empty((2 * n, 64), dtype=torch.uint8, device=self.device)
+        count = n if rows is None else rows.numel()
+        exc = np.zeros(max(count, 1), dtype=np.uint32)
+        n_exc = C.c_uint32(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        if salts is not None:
+            assert salts.dtype == torch.uint8 and salts.is_contiguous() and salts.shape[0] == n
+        self.check(self.lib.b2s_merkle_rows(vp(ptrs), vp(modes), len(planes), n, vp(tpl), vp(seg), len(seg) - 2,
+                                            _ptr(salts) if salts is not None else None,
+                                            salts.shape[1] if salts is not None else 0, vp(pre), len(salt_pre), vp(suf),
+                                            len(salt_suf), _ptr(rows) if rows is not None else None,
+                                            0 if rows is None else count, _ptr(nodes), 1 if build_upper else 0, vp(exc),
+                                            C.byref(n_exc), self.stream_ptr()))
+        return nodes, exc[:n_exc.value].copy()
+
     def merkle_upper(self, nodes):
         """inner nodes above the digests in slots [npo2, 2 npo2) of `nodes` ((2 npo2, 64) uint8), in place"""
         self.check(self.lib.b2s_merkle_upper(_ptr(nodes), nodes.shape[0] // 2, self.stream_ptr()))

@@ -95,7 +95,11 @@ class Glue:
 
     def remember_planes(self, values, planes):
         if self._kept is not None and len(values):
-            self._kept[id(values)] = (values, planes, values[0], values[-1])
+            n = len(values)
+            probe = sorted({(n * k) // 8 for k in range(8)} | {n - 1})  # positions whose identity is re-checked
+            ent = (values, planes, probe, [values[i] for i in probe])
+            self._kept[id(values)] = ent
+            self._kept[("first", id(values[0]))] = ent  # rows zipped from codewords find their columns again
 
     def planes_of(self, codeword):
         """device planes behind a codeword, or None"""
@@ -104,7 +108,8 @@ class Glue:
         ent = self._kept.get(id(codeword)) if self._kept is not None else None
         if ent is None or ent[0] is not codeword or len(codeword) != ent[1].shape[1]:
             return None
-        if codeword[0] is not ent[2] or codeword[-1] is not ent[3]:
+        # the list is the caller's: a replaced element (first, last or a few in between) drops the link
+        if any(codeword[i] is not e for i, e in zip(ent[2], ent[3])):
             return None
         return ent[1]
 
@@ -628,9 +633,6 @@ class Glue:
         pickles them and the device hashes the byte strings and builds the tree (b2s_merkle_blobs).
         open / verify / root stay the reference's: they only index .leafs and .nodes."""
         n = len(data_array)
-        if isinstance(data_array, DeviceCodeword) and leaf_cache is None and n > 0 and n & (n - 1) == 0:
-            # a codeword that never left the device: its lazily materialised elements ARE the leaves
-            leaf_cache, device_planes, canonical = data_array, data_array._planes, True
         tree.num_leafs = n
         npo2 = 1
         while npo2 < n:
@@ -639,9 +641,86 @@ class Glue:
         tree.leafs = [(element, urandom(24)) for element in data_array]  # code/salted_merkle.py:25
         # code/salted_merkle.py:23: with no leaves the reference's own consistency assert fires
         assert n != 0, "in SaltedMerkle.__init__, next_power_of_two = 0 =/= 1 << self.depth = 1"
-        dumps = pickle.dumps
-        tree._device_nodes = self.engine.merkle_blobs([dumps(e) + dumps(salt) for e, salt in tree.leafs])
+        nodes = self._row_tree(tree.leafs) if n == npo2 else None
+        if nodes is None:  # rows the device templates cannot express: the host pickles, the device hashes
+            dumps = pickle.dumps
+            nodes = self.engine.merkle_blobs([dumps(e) + dumps(salt) for e, salt in tree.leafs])
+        tree._device_nodes = nodes
         tree.nodes = NodeView(self.engine, tree._device_nodes, npo2, n)
+
+    MAX_ROW_SHAPES = 32
+
+    def _row_columns(self, rows):
+        """device planes behind every column of zipped rows (list of (n,) views in row order), or None.
+        Columns that came out of a device op inside keep_planes() are read in place; others are marshalled
+        after checking that the whole column has ONE identity pattern (the row template assumes it)."""
+        B, n = self.B, len(rows)
+        first = rows[0]
+        if type(first) is not tuple or not first or any(type(r) is not tuple or len(r) != len(first) for r in rows):
+            return None
+        planes = []
+        for k, e in enumerate(first):
+            ent = self._kept.get(("first", id(e))) if self._kept is not None else None
+            if ent is not None and len(ent[0]) == n and ent[1].shape[1] == n and \
+                    all(rows[i][k] is v and ent[0][i] is v for i, v in zip(ent[2], ent[3])):
+                col = ent[1]
+            else:
+                column = [r[k] for r in rows]
+                if B.is_bfe(e):
+                    f = e.field
+                    if not all(type(v) is B.BaseFieldElement and v.field is f for v in column):
+                        return None
+                    col = self.engine.upload(B.bfe_to_np(column))
+                elif B.is_xfe(e) and B.xfe_canonical(column, e.field):
+                    col = self.engine.upload(B.xfe_to_np(column))
+                else:
+                    return None
+            if col.shape[0] != (1 if B.is_bfe(e) else 3) or col.stride(1) != 1:
+                return None
+            planes += [col[q] for q in range(col.shape[0])]
+        return planes
+
+    def _row_tree(self, leafs):
+        """Device tree over salted rows: the row pickle is a per-tree byte template
+        derived from a sample row; the device splices the integers of the codeword planes and the salts.
+        Returns the node tensor, or None when the rows cannot be expressed (the caller then pickles)."""
+        from . import marshal
+        n = len(leafs)
+        rows = [leaf[0] for leaf in leafs]
+        salt0 = leafs[0][1]
+        frame = marshal.salt_frame(salt0) if type(salt0) is bytes else None
+        if frame is None or any(type(leaf[1]) is not bytes or len(leaf[1]) != len(salt0) for leaf in leafs):
+            return None
+        tpl = marshal.row_template(self.B, rows[0])
+        if tpl is None:
+            return None
+        planes = self._row_columns(rows)
+        if planes is None or len(planes) != len(tpl.modes):
+            return None
+        eng = self.engine
+        salts = torch.from_numpy(np.frombuffer(b"".join(leaf[1] for leaf in leafs), dtype=np.uint8)
+                                 .reshape(n, len(salt0)).copy()).to(eng.device)
+        # a couple of rows rendered on the host as well: the template must reproduce the caller's pickler
+        for i in {0, n // 2, n - 1}:
+            t = tpl if marshal.row_signature(self.B, rows[i]) == tpl.signature else marshal.row_template(self.B, rows[i])
+            if t is None or t.render(marshal.row_values(rows[i])) != pickle.dumps(rows[i]):
+                return None
+        nodes, exc = eng.merkle_rows(planes, tpl.modes, tpl.tpl, tpl.seg_off, n, salts, frame[0], frame[1])
+        shapes = 1
+        while len(exc):  # rows of another shape (trimmed extension-field coefficients): one more template each
+            shapes += 1
+            t = marshal.row_template(self.B, rows[int(exc[0])])
+            if t is None or shapes > self.MAX_ROW_SHAPES:
+                return None
+            todo = torch.from_numpy(np.sort(exc).astype(np.int32)).to(eng.device)
+            nodes, rest = eng.merkle_rows(planes, t.modes, t.tpl, t.seg_off, n, salts, frame[0], frame[1], rows=todo,
+                                          nodes=nodes, build_upper=False)
+            if len(rest) == len(exc):
+                return None  # no progress: the sample row itself does not fit its own template
+            exc = rest
+            if not len(exc) and n > 1:
+                eng.merkle_upper(nodes)
+        return nodes
 
     # ------------------------------------------------------------------ code/fri.py Fri
     def fri_commit(self, fri, codeword, proof_stream, round_index=0, Merkle=None):

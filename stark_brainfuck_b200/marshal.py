@@ -214,3 +214,136 @@ def templates_from_marker_pickles(pickles, n_slots, trim):
         raise ValueError("leaf templates need %d bytes (max %d)" % (len(blob), TPL_MAX_BYTES))
     C.memmove(t.bytes, bytes(blob), len(blob))
     return t
+
+
+# ---- row templates: pickle.dumps(tuple of field elements) with the integers cut out ------------------------
+def pickle_uint(v):
+    """CPython _pickle.c save_long, protocol 4, for 0 <= v < 2^64"""
+    if v < 256:
+        return b"K" + bytes([v])
+    if v < 65536:
+        return b"M" + v.to_bytes(2, "little")
+    if v < 1 << 31:
+        return b"J" + v.to_bytes(4, "little")
+    nb = (v.bit_length() >> 3) + 1
+    return b"\x8a" + bytes([nb]) + v.to_bytes(nb, "little")
+
+
+def _row_marker(j):
+    return 0xC3A5000000005AC3 | (j << 16)  # >= 2^63: pickled as LONG1 with 9 payload bytes
+
+
+class RowTemplate:
+    """Byte template of pickle.dumps(row) for the rows of a salted tree (code/salted_merkle.py:31): `tpl` cut into
+    n_slots + 1 segments (`seg_off`) around the integers; `modes` has one entry per device plane of the row's
+    columns in order (0 integer slot, 1 integer slot that must be non-zero, 2 trimmed coefficient that must be
+    zero -- include/b2s.h b2s_merkle_rows)."""
+
+    def __init__(self, signature, modes, tpl, seg_off):
+        self.signature, self.modes, self.tpl, self.seg_off = signature, modes, tpl, seg_off
+
+    def render(self, values):
+        """the pickle for the given slot integers (host check of the template)"""
+        body = b"".join(self.tpl[self.seg_off[j]:self.seg_off[j + 1]] + pickle_uint(v) for j, v in enumerate(values))
+        body += self.tpl[self.seg_off[len(values)]:self.seg_off[len(values) + 1]]
+        return b"\x80\x04\x95" + len(body).to_bytes(8, "little") + body
+
+
+def row_signature(binding, row):
+    """per element: -1 for a BaseFieldElement, the number of coefficients for an ExtensionFieldElement;
+    None when the row holds anything else or has an object graph the template cannot express"""
+    if type(row) is not tuple:
+        return None
+    sig, seen = [], set()
+    for e in row:
+        if binding.is_bfe(e):
+            if list(e.__dict__) != ["value", "field"] or not isinstance(e.value, int) or not 0 <= e.value < 1 << 64:
+                return None
+            sig.append(-1)
+            objs = [e]
+        elif binding.is_xfe(e):
+            if list(e.__dict__) != ["polynomial", "field"] or type(e.polynomial) is not binding.Polynomial or \
+                    list(e.polynomial.__dict__) != ["coefficients"] or type(e.polynomial.coefficients) is not list:
+                return None
+            co = e.polynomial.coefficients
+            if len(co) > 3 or (co and co[-1].value == 0):
+                return None
+            for c in co:
+                if not binding.is_bfe(c) or list(c.__dict__) != ["value", "field"] or not isinstance(c.value, int) \
+                        or not 0 <= c.value < 1 << 64:
+                    return None
+            sig.append(len(co))
+            objs = [e, e.polynomial, co] + list(co)
+        else:
+            return None
+        for o in objs:  # an object met twice would be pickled as a memo reference
+            if id(o) in seen:
+                return None
+            seen.add(id(o))
+    return tuple(sig)
+
+
+def row_values(row):
+    """the slot integers of a row, in pickle order"""
+    vals = []
+    for e in row:
+        if "value" in e.__dict__:
+            vals.append(e.value)
+        else:
+            vals += [c.value for c in e.polynomial.coefficients]
+    return vals
+
+
+def row_template(binding, row):
+    """RowTemplate of `row`'s shape and identity pattern (same classes, same `field` objects), checked against
+    pickle.dumps(row) itself; None if the row cannot be expressed."""
+    sig = row_signature(binding, row)
+    if sig is None:
+        return None
+    B, Pn, X = binding.BaseFieldElement, binding.Polynomial, binding.ExtensionFieldElement
+
+    def bfe(value, field):
+        o = B.__new__(B)
+        o.__dict__ = {"value": value, "field": field}
+        return o
+    fake, modes, j = [], [], 0
+    for e, k in zip(row, sig):
+        if k < 0:
+            fake.append(bfe(_row_marker(j), e.field))
+            modes.append(0)
+            j += 1
+        else:
+            co = [bfe(_row_marker(j + i), c.field) for i, c in enumerate(e.polynomial.coefficients)]
+            j += k
+            p = Pn.__new__(Pn)
+            p.__dict__ = {"coefficients": co}
+            x = X.__new__(X)
+            x.__dict__ = {"polynomial": p, "field": e.field}
+            fake.append(x)
+            modes += [0] * (k - 1) + [1] * (k > 0) + [2] * (3 - k)
+    pk = pickle.dumps(tuple(fake))
+    if pk[:3] != b"\x80\x04\x95" or int.from_bytes(pk[3:11], "little") != len(pk) - 11:
+        return None  # not a single protocol-4 frame (another interpreter default): the caller pickles on the host
+    rest, blob, seg_off = pk[11:], bytearray(), [0]
+    for i in range(j):
+        mark = pickle_uint(_row_marker(i))
+        if rest.count(mark) != 1:
+            return None
+        head, rest = rest.split(mark)
+        blob += head
+        seg_off.append(len(blob))
+    blob += rest
+    seg_off.append(len(blob))
+    t = RowTemplate(sig, np.array(modes, dtype=np.uint8), bytes(blob), np.array(seg_off, dtype=np.uint32))
+    if t.render(row_values(row)) != pickle.dumps(row):
+        return None
+    return t
+
+
+def salt_frame(salt):
+    """(prefix, suffix) of pickle.dumps(salt) around the salt bytes"""
+    pk = pickle.dumps(salt)
+    i = pk.find(salt)
+    if type(salt) is not bytes or i < 0 or pk.count(salt) != 1:
+        return None
+    return pk[:i], pk[i + len(salt):]

@@ -2,8 +2,8 @@
 
 Where the reference checkout is available, use stark_brainfuck_b200.dropin.install() and keep
 calling the reference's own modules.  Where it is not (the GPU box), this package offers the
-same module / class / function names -- algebra, univariate, extension_field, ntt, merkle, ip,
-fri -- so code and tests written against the reference read the same.
+same module / class / function names -- algebra, univariate, extension_field, ntt, merkle,
+salted_merkle, ip, fri -- so code and tests written against the reference read the same.
 
 Pickle is the reference's wire format and records module names, so byte-identical Merkle
 leaves and transcripts need these classes to be importable under the reference's BARE module
@@ -13,7 +13,7 @@ unregister() removes them.
 import sys
 import types
 
-from . import fri, hostmodel, merkle, ntt
+from . import fri, hostmodel, merkle, ntt, salted_merkle
 from ..glue import Glue
 from ..marshal import Binding
 
@@ -36,9 +36,9 @@ univariate = _module("univariate", _UNIVARIATE)
 extension_field = _module("extension_field", _EXTENSION)
 ip = _module("ip", ("ProofStream", "pickle", "shake_256"))
 
-NAMES = ("algebra", "univariate", "extension_field", "ntt", "merkle", "ip", "fri")
+NAMES = ("algebra", "univariate", "extension_field", "ntt", "merkle", "salted_merkle", "ip", "fri")
 _MODS = {"algebra": algebra, "univariate": univariate, "extension_field": extension_field, "ntt": ntt,
-         "merkle": merkle, "ip": ip, "fri": fri}
+         "merkle": merkle, "salted_merkle": salted_merkle, "ip": ip, "fri": fri}
 
 binding = Binding.from_modules(algebra, univariate, extension_field)
 field = algebra.BaseField.main()

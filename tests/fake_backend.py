@@ -114,6 +114,28 @@ class FakeLib:
         _u8(_addr(d_nodes), 128 * npo2)[:] = orc.merkle_blobs(blobs).reshape(-1)
         return 0
 
+    def b2s_merkle_rows(self, h_planes, h_modes, n_planes, n, h_tpl, h_seg_off, n_slots, d_salts, salt_len, h_pre,
+                        pre_len, h_suf, suf_len, d_rows, n_rows, d_nodes, build_upper, h_exc, h_n_exc, stream):
+        self.launches += 1
+        ptrs = _u64(_addr(h_planes), n_planes)
+        planes = [_u64(int(ptrs[p]), n) for p in range(n_planes)]
+        modes = _u8(_addr(h_modes), n_planes)
+        seg = np.ctypeslib.as_array((C.c_uint32 * (n_slots + 2)).from_address(_addr(h_seg_off)))
+        tpl = bytes(_u8(_addr(h_tpl), int(seg[n_slots + 1]))) if seg[n_slots + 1] else b""
+        salts = _u8(_addr(d_salts), n * salt_len).reshape(n, salt_len) if _addr(d_salts) else None
+        rows = (np.ctypeslib.as_array((C.c_uint32 * n_rows).from_address(_addr(d_rows))) if _addr(d_rows) else None)
+        nodes = _u8(_addr(d_nodes), 128 * n).reshape(2 * n, 64)
+        if rows is None:
+            nodes[0] = 0
+        exc = orc.row_leaves(planes, modes, tpl, seg, n, nodes, salts, bytes(_u8(_addr(h_pre), pre_len)) if pre_len else b"",
+                             bytes(_u8(_addr(h_suf), suf_len)) if suf_len else b"", rows)
+        if len(exc):
+            np.ctypeslib.as_array((C.c_uint32 * len(exc)).from_address(_addr(h_exc)))[:] = exc
+        h_n_exc._obj.value = len(exc)
+        if build_upper and not len(exc) and n > 1:
+            nodes[:] = orc.merkle_upper(nodes.copy())
+        return 0
+
     def b2s_merkle_upper(self, d_nodes, npo2, stream):
         self.launches += 1
         view = _u8(_addr(d_nodes), 128 * npo2).reshape(-1, 64)

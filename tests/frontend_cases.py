@@ -16,8 +16,9 @@ M = golden("merkle.json")
 FS = golden("fri_small.json")
 
 
-def make_env(algebra, univariate, extension_field, ntt, merkle, ip, fri):
+def make_env(algebra, univariate, extension_field, ntt, merkle, ip, fri, salted_merkle=None):
     env = types.SimpleNamespace()
+    env.salted_merkle = salted_merkle
     env.BaseField, env.BaseFieldElement = algebra.BaseField, algebra.BaseFieldElement
     env.Polynomial = univariate.Polynomial
     env.ExtensionField, env.ExtensionFieldElement = extension_field.ExtensionField, extension_field.ExtensionFieldElement
@@ -404,3 +405,58 @@ def case_quotients_glue(env, glue):
         if scope:
             assert any(isinstance(k, tuple) for k in glue._kept)  # the assembled table planes were kept
             scope.__exit__(None, None, None)
+
+
+def salted_rows(env, case):
+    """the rows of a tests/golden/salted.json case, rebuilt with one BaseField object per field_id"""
+    fields, cols = {}, []
+    for c in case["columns"]:
+        if c["kind"] == "b":
+            f = fields.setdefault(c["field_id"], env.BaseField.main())
+            cols.append([env.BaseFieldElement(v, f) for v in c["values"]])
+        else:
+            cols.append([X(env, *t) for t in c["values"]])
+    return cols, list(zip(*cols))
+
+
+def case_salted(env, glue=None):
+    """SaltedMerkle over zipped rows (code/salted_merkle.py, code/brainfuck_stark.py:178-199)
+    against the reference's own trees (tests/golden/salted.json): roots, every node, openings."""
+    sm = env.salted_merkle
+    old = sm.urandom
+    try:
+        for case in golden("salted.json")["cases"]:
+            cols, rows = salted_rows(env, case)
+            n = case["n"]
+            for kept in (False, True) if glue is not None else (False,):
+                R = random.Random(case["salt_seed"])
+                sm.urandom = lambda k: bytes(R.getrandbits(8) for _ in range(k))
+                if kept:  # columns that are already on the device, as inside BrainfuckStark.prove
+                    with glue.keep_planes():
+                        for col in cols:
+                            arr = (glue.B.bfe_to_np(col).reshape(1, -1) if glue.B.is_bfe(col[0]) else glue.B.xfe_to_np(col))
+                            glue.remember_planes(col, glue.engine.upload(arr))
+                        t = sm.SaltedMerkle(rows)
+                else:
+                    t = sm.SaltedMerkle(rows)
+                assert [s_.hex() for _, s_ in t.leafs] == case["salts"]
+                assert t.root().hex() == case["root"], case["name"]
+                assert [t.nodes[n + i].hex() for i in range(n)] == case["leaf_digests"]
+                assert hashlib.sha256(b"".join(t.nodes[1:])).hexdigest() == case["nodes_sha256"]
+                salt, path = t.open(case["open_index"])
+                assert [d.hex() for d in path] == case["open_path"] and salt.hex() == case["salts"][case["open_index"]]
+                assert sm.SaltedMerkle.verify(t.root(), case["open_index"], salt, path, rows[case["open_index"]])
+                assert t.leafs[0][0] is rows[0] and t.num_leafs == n and t.depth == n.bit_length() - 1
+        # leaves the row templates cannot express (not tuples of field elements; not a power of two): host pickling
+        R = random.Random(5)
+        sm.urandom = lambda k: bytes(R.getrandbits(8) for _ in range(k))
+        for data in ([("a", 1), ("b", 2), ("c", 3)], [env.BaseFieldElement(i, env.field) for i in range(4)],
+                     [(env.BaseFieldElement(i, env.field), "x") for i in range(2)]):
+            t = sm.SaltedMerkle(data)
+            want = [hashlib.blake2b(pickle.dumps(e) + pickle.dumps(s_)).digest() for e, s_ in t.leafs]
+            npo2 = 1 << t.depth
+            assert [t.nodes[npo2 + i] for i in range(len(data))] == want
+            salt, path = t.open(1)
+            assert sm.SaltedMerkle.verify(t.root(), 1, salt, path, data[1])
+    finally:
+        sm.urandom = old

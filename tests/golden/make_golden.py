@@ -11,7 +11,7 @@ little-endian u64 values; ExtensionFieldElement = c0,c1,c2 with trimmed
 coefficients zero-filled, elements in list order.
 
 Usage:  python tests/golden/make_golden.py <group> [...]
-Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination  lde  air
+Groups: small  ntt_big  xntt_big  fri_small  fri_16  fri_18  fri_20  bfs  quotients  combination  lde  air  salted
 Heavy groups are meant to run in the background, one process each.
 """
 import hashlib
@@ -680,6 +680,65 @@ def group_combination():
     dump("combination.json", out)
 
 
+
+def group_salted():
+    """code/salted_merkle.py over zipped rows, the way BrainfuckStark.prove builds its base and extension trees
+    (code/brainfuck_stark.py:178-180, :197-199): tuples of elements that carry DIFFERENT field objects, seeded
+    salts.  Columns are stored as plain integers (extension-field columns as coefficient triples); the test
+    rebuilds the objects with one field object per `field_id`."""
+    import salted_merkle
+    edge = [0, 1, 255, 256, 65535, 65536, (1 << 31) - 1, 1 << 31, (1 << 32) - 1, 1 << 32, (1 << 39) - 1, 1 << 39,
+            (1 << 63) - 1, 1 << 63, P - 1, 12345678901234567]
+    cases = []
+
+    def run(name, n, columns, seed):
+        fields = {}
+        R = random.Random(seed)
+        cols = []
+        for c in columns:
+            if c["kind"] == "b":
+                f = fields.setdefault(c["field_id"], BaseField.main())
+                cols.append([BaseFieldElement(v, f) for v in c["values"]])
+            else:
+                cols.append([X(*t) for t in c["values"]])
+        rows = list(zip(*cols))
+        salted_merkle.urandom = lambda k: bytes(R.getrandbits(8) for _ in range(k))
+        tree = salted_merkle.SaltedMerkle(rows)
+        salted_merkle.urandom = os.urandom
+        salt, path = tree.open(n // 3)
+        assert salted_merkle.SaltedMerkle.verify(tree.root(), n // 3, salt, path, rows[n // 3])
+        cases.append({"name": name, "n": n, "columns": columns, "salt_seed": seed,
+                      "salts": [s_.hex() for _, s_ in tree.leafs], "root": tree.root().hex(),
+                      "nodes_sha256": hashlib.sha256(b"".join(tree.nodes[1:])).hexdigest(),
+                      "leaf_digests": [tree.nodes[n + i].hex() for i in range(n)],
+                      "preimage_last_row": (pickle.dumps(rows[-1]) + pickle.dumps(tree.leafs[-1][1])).hex(),
+                      "open_index": n // 3, "open_path": [d.hex() for d in path]})
+
+    R = random.Random(4242)
+    rb = lambda n: [R.randrange(P) for _ in range(n)]  # noqa: E731
+    rx = lambda n: [[R.randrange(P) for _ in range(3)] for _ in range(n)]  # noqa: E731
+    # the base tree's shape: randomizer (extension field) first, then base columns of several tables
+    run("base_rows", 16, [{"kind": "x", "values": rx(16)}, {"kind": "b", "field_id": 0, "values": rb(16)},
+                          {"kind": "b", "field_id": 0, "values": edge}, {"kind": "b", "field_id": 1, "values": rb(16)},
+                          {"kind": "b", "field_id": 2, "values": [i % 3 for i in range(16)]}], 77)
+    # the extension tree's shape: extension-field columns only
+    run("extension_rows", 8, [{"kind": "x", "values": rx(8)} for _ in range(4)], 78)
+    # rows of different pickle shapes: trimmed coefficients (code/extension_field.py:6-9), zero elements
+    tr = rx(8)
+    tr[2] = [5, 0, 0]
+    tr[3] = [0, 0, 0]
+    tr[5] = [7, 9, 0]
+    tr2 = rx(8)
+    tr2[0] = [0, 0, 0]
+    tr2[5] = [1, 0, 0]
+    run("trimmed_rows", 8, [{"kind": "x", "values": tr}, {"kind": "b", "field_id": 0, "values": rb(8)},
+                            {"kind": "x", "values": tr2}], 79)
+    # a first column that is constant one (one coefficient in every row), two rows only, one row only
+    run("constant_first", 4, [{"kind": "x", "values": [[1, 0, 0]] * 4}, {"kind": "x", "values": rx(4)}], 80)
+    run("two_rows", 2, [{"kind": "b", "field_id": 0, "values": rb(2)}, {"kind": "x", "values": rx(2)}], 81)
+    run("one_row", 1, [{"kind": "b", "field_id": 0, "values": rb(1)}], 82)
+    dump("salted.json", {"cases": cases})
+
 if __name__ == "__main__":
     for grp in sys.argv[1:]:
         if grp == "small":
@@ -712,5 +771,7 @@ if __name__ == "__main__":
             group_combination()
         elif grp == "quotients":
             group_quotients()
+        elif grp == "salted":
+            group_salted()
         else:
             raise SystemExit("unknown group " + grp)

@@ -12,7 +12,7 @@ import frontend_cases as fc
 @pytest.fixture(scope="module")
 def env(reference_dropin):
     mods = [importlib.import_module(m) for m in
-            ("algebra", "univariate", "extension_field", "ntt", "merkle", "ip", "fri")]
+            ("algebra", "univariate", "extension_field", "ntt", "merkle", "ip", "fri", "salted_merkle")]
     e = fc.make_env(*mods)
     e.glue = reference_dropin
     return e
@@ -287,6 +287,10 @@ def test_salted_merkle_matches_reference(reference_dropin):
     assert got == want
     with pytest.raises(AssertionError):
         salted_merkle.SaltedMerkle([])
+
+
+def test_salted_row_trees_golden(env):
+    fc.case_salted(env, env.glue)
 
 
 def test_nonlinear_combination_matches_reference_block(env):

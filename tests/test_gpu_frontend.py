@@ -15,7 +15,7 @@ from util import golden, have_golden  # noqa: E402
 @pytest.fixture(scope="module")
 def env(mirror_gpu):
     m = mirror_gpu
-    return fc.make_env(m.algebra, m.univariate, m.extension_field, m.ntt, m.merkle, m.ip, m.fri)
+    return fc.make_env(m.algebra, m.univariate, m.extension_field, m.ntt, m.merkle, m.ip, m.fri, m.salted_merkle)
 
 
 def test_ntt_golden(env):
@@ -75,3 +75,7 @@ def test_table_lde(env, mirror_gpu):
 
 def test_quotients_through_the_glue(env, mirror_gpu):
     fc.case_quotients_glue(env, mirror_gpu.glue())
+
+
+def test_salted_row_trees(env, mirror_gpu):
+    fc.case_salted(env, mirror_gpu.glue())

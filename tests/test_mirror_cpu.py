@@ -8,7 +8,7 @@ import frontend_cases as fc
 @pytest.fixture(scope="module")
 def env(mirror_cpu):
     m = mirror_cpu
-    return fc.make_env(m.algebra, m.univariate, m.extension_field, m.ntt, m.merkle, m.ip, m.fri)
+    return fc.make_env(m.algebra, m.univariate, m.extension_field, m.ntt, m.merkle, m.ip, m.fri, m.salted_merkle)
 
 
 def test_ntt_golden(env):
@@ -71,3 +71,7 @@ def test_table_lde(env, mirror_cpu):
 
 def test_quotients_through_the_glue(env, mirror_cpu):
     fc.case_quotients_glue(env, mirror_cpu.glue())
+
+
+def test_salted_row_trees(env, mirror_cpu):
+    fc.case_salted(env, mirror_cpu.glue())
