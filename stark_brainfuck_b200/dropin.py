@@ -27,7 +27,7 @@ import textwrap
 import warnings
 
 from .glue import Glue
-from .marshal import Binding
+from .marshal import Binding, bulk_allocation
 
 _state = None
 
@@ -183,7 +183,10 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
             guarded = scope["prove"]
 
             def prove(self, *args, **kwargs):
-                with glue.keep_planes():  # codewords stay readable on the device for the length of one proof
+                # codewords stay readable on the device for the length of one proof; the cyclic collector is paused:
+                # a proof allocates tens of millions of acyclic element objects and every generation-0 overflow
+                # would rescan them (marshal.bulk_allocation)
+                with glue.keep_planes(), bulk_allocation():
                     return guarded(self, *args, **kwargs)
             prove.__wrapped__ = guarded
             prove.__doc__ = guarded.__doc__

@@ -42,24 +42,55 @@ class Engine:
             return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         return C.c_void_p(0)
 
+    # Device-memory primitives.  Everything the glue does to device memory outside the C ABI goes through
+    # these methods (allocation, fill, host -> device, device -> host, device -> device), so that a recording
+    # engine (tests/trace_backend.py) sees the complete command stream of a proof.
+    def alloc(self, shape, dtype=torch.int64, zero=False):
+        return (torch.zeros if zero else torch.empty)(tuple(shape), dtype=dtype, device=self.device)
+
+    def upload_into(self, dst, arr):
+        """host numpy array -> the device view `dst` (same shape; uint64 data into int64 views)"""
+        a = np.ascontiguousarray(arr)
+        if a.dtype == np.uint64:
+            a = a.view(np.int64)
+        if not a.flags.writeable:  # e.g. np.frombuffer over bytes: torch refuses to wrap read-only memory
+            a = a.copy()
+        dst.copy_(torch.from_numpy(a).reshape(dst.shape))
+        return dst
+
+    def zero(self, dst):
+        dst.zero_()
+        return dst
+
+    def copy(self, dst, src):
+        """device -> device"""
+        dst.copy_(src)
+        return dst
+
     def upload(self, arr, pinned=False):
         """numpy uint64 array (n,) or (q, n) -> device int64 tensor (q, n)"""
         a = np.ascontiguousarray(arr, dtype=np.uint64)
         if a.ndim == 1:
             a = a.reshape(1, -1)
-        t = torch.from_numpy(a.view(np.int64))
-        if self.device.type == "cuda":
-            if pinned:
-                t = t.pin_memory()
-            return t.to(self.device, non_blocking=pinned)
-        return t.clone()
+        if pinned and self.device.type == "cuda":
+            t = torch.from_numpy(a.view(np.int64)).pin_memory()
+            return t.to(self.device, non_blocking=True)
+        return self.upload_into(self.alloc(a.shape), a)
+
+    def upload_bytes(self, data):
+        """bytes / uint8 array -> device uint8 tensor of the same shape"""
+        a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+        return self.upload_into(self.alloc(a.shape, torch.uint8), a)
 
     def download(self, t):
         """device tensor -> numpy uint64 array with the same shape (synchronises)"""
         return t.detach().cpu().contiguous().numpy().view(np.uint64)
 
     def empty(self, planes, n):
-        return torch.empty((planes, n), dtype=torch.int64, device=self.device)
+        return self.alloc((planes, n))
+
+    def zeros(self, planes, n):
+        return self.alloc((planes, n), zero=True)
 
     def check(self, rc):
         _lib.check(self.lib, rc)
@@ -106,7 +137,7 @@ class Engine:
         """code/univariate.py:168-169.  factor: int (base field) or 3 ints (extension field)"""
         q, n = x.shape
         f = (C.c_uint64 * 3)(*([factor, 0, 0] if isinstance(factor, int) else list(factor)))
-        out = torch.empty_like(x)
+        out = self.alloc(x.shape)
         self.check(self.lib.b2s_scale(_ptr(x), x.stride(0), _ptr(out), out.stride(0), n, q, f, self.stream_ptr()))
         return out
 
@@ -124,7 +155,7 @@ class Engine:
         """code/merkle.py:8-41 over field-element leaves; returns nodes (2n, 64) uint8"""
         q, n = planes.shape
         assert q == tpl.n_slots
-        nodes = torch.empty((2 * n, 64), dtype=torch.uint8, device=self.device)
+        nodes = self.alloc((2 * n, 64), torch.uint8)
         self.check(self.lib.b2s_merkle_field(_ptr(planes), planes.stride(0), n, C.byref(tpl), _ptr(nodes),
                                              self.stream_ptr()))
         return nodes
@@ -137,10 +168,9 @@ class Engine:
             npo2 *= 2
         offs = np.zeros(n + 1, dtype=np.uint64)
         offs[1:] = np.cumsum([len(b) for b in blobs])
-        data = np.frombuffer(b"".join(blobs) + b"\0" * 8, dtype=np.uint8)
-        d_data = torch.from_numpy(data.copy()).to(self.device)
+        d_data = self.upload_bytes(b"".join(blobs) + b"\0" * 8)
         d_offs = self.upload(offs)
-        nodes = torch.empty((2 * npo2, 64), dtype=torch.uint8, device=self.device)
+        nodes = self.alloc((2 * npo2, 64), torch.uint8)
         self.check(self.lib.b2s_merkle_blobs(_ptr(d_data), _ptr(d_offs), n, npo2, _ptr(nodes), self.stream_ptr()))
         return nodes
 
@@ -158,7 +188,7 @@ class Engine:
         pre = np.frombuffer(bytes(salt_pre) + b"\0", dtype=np.uint8)
         suf = np.frombuffer(bytes(salt_suf) + b"\0", dtype=np.uint8)
         if nodes is None:
-            nodes = torch.empty((2 * n, 64), dtype=torch.uint8, device=self.device)
+            nodes = self.alloc((2 * n, 64), torch.uint8)
         count = n if rows is None else rows.numel()
         exc = np.zeros(max(count, 1), dtype=np.uint32)
         n_exc = C.c_uint32(0)
@@ -236,7 +266,7 @@ class Engine:
         q, N = cw.shape
         assert q == 3
         nxt = self.empty(3, N // 2)
-        nodes = torch.empty((N, 64), dtype=torch.uint8, device=self.device) if tpl is not None else None
+        nodes = self.alloc((N, 64), torch.uint8) if tpl is not None else None
         a = (C.c_uint64 * 3)(*[int(v) for v in alpha])
         self.check(self.lib.b2s_fri_fold(_ptr(cw), cw.stride(0), N, a, offset, omega, _ptr(nxt), nxt.stride(0),
                                          C.byref(tpl) if tpl is not None else None,
@@ -254,7 +284,7 @@ class Engine:
         nc = len(mono_off) - 1
         coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 3)
         factors = np.ascontiguousarray(factors, dtype=np.uint32).reshape(len(coeffs), -1)
-        out = torch.empty((nc, 3, N), dtype=torch.int64, device=self.device)
+        out = self.alloc((nc, 3, N))
         flag = C.c_int(0)
         self.check(self.lib.b2s_quotients(_ptr(cw), N, width, shift, nc, mono_off.ctypes.data_as(C.c_void_p),
                                           coeffs.ctypes.data_as(C.c_void_p), factors.ctypes.data_as(C.c_void_p),

@@ -29,7 +29,8 @@ class Glue:
         self._engine = engine
         self._xtpl = {}  # id(xfield) -> (xfield, templates)
         self._btpl = {}  # id(field)  -> (field, templates)
-        self._kept = None  # id(list) -> (list, device planes, first, last) inside keep_planes()
+        self._kept = None  # id(list) -> (list, device planes, probe positions, probe elements) inside keep_planes()
+        self.coset_routed = 0  # evaluate_domain calls that became one coset transform
 
     @property
     def engine(self):
@@ -100,6 +101,8 @@ class Glue:
             ent = (values, planes, probe, [values[i] for i in probe])
             self._kept[id(values)] = ent
             self._kept[("first", id(values[0]))] = ent  # rows zipped from codewords find their columns again
+            for i in probe:  # ... and so do element-wise lifts of a base-field codeword (see lifted_planes_of)
+                self._kept[("elem", id(values[i]))] = (ent, i)
 
     def planes_of(self, codeword):
         """device planes behind a codeword, or None"""
@@ -111,6 +114,33 @@ class Glue:
         # the list is the caller's: a replaced element (first, last or a few in between) drops the link
         if any(codeword[i] is not e for i, e in zip(ent[2], ent[3])):
             return None
+        return ent[1]
+
+    def lifted_planes_of(self, codeword):
+        """The base-field plane behind `[xfield.lift(c) for c in base_codeword]` -- what every Table.extend of the
+        reference does to its base codewords (e.g. code/io_table.py:106-107) -- or None.  lift wraps the base
+        element ITSELF as the only coefficient (code/extension_field.py:113-116; a zero is trimmed away,
+        :6-9), so the lifted list is recognised by identity at the probe positions of the kept base codeword."""
+        if self._kept is None or type(codeword) is not list or not codeword:
+            return None
+        ent = None
+        for i in sorted({0, len(codeword) - 1, len(codeword) // 2}):
+            e = codeword[i]
+            if not self.B.is_xfe(e):
+                return None
+            co = e.polynomial.coefficients
+            if len(co) == 1:
+                hit = self._kept.get(("elem", id(co[0])))
+                if hit is not None and hit[1] == i:
+                    ent = hit[0]
+                    break
+        if ent is None or len(ent[0]) != len(codeword) or ent[1].shape[0] != 1:
+            return None
+        for i, base in zip(ent[2], ent[3]):
+            co = codeword[i].polynomial.coefficients if self.B.is_xfe(codeword[i]) else None
+            if co is None or ent[0][i] is not base or not ((len(co) == 1 and co[0] is base) or
+                                                             (len(co) == 0 and base.value == 0)):
+                return None
         return ent[1]
 
     # ------------------------------------------------------------------ code/ntt.py
@@ -132,16 +162,19 @@ class Glue:
         share = 0
         if kind == "x" and not inverse:
             share = self._shared_output_period(arr, n)
-            if share == 1:
-                return self._lone_coefficient_ntt(lone_source if lone_source is not None else first, w, n)
         out = self.engine.ntt(self.engine.upload(arr), _ilog2(n), w, offset=offset, inverse=inverse)
-        if share:
+        if share == 1:
+            values = self._lone_coefficient_ntt(lone_source if lone_source is not None else first, w, n)
+        elif share:
             # outputs i and i + share are the same sub-transform output with a zero odd partner all the
             # way up: distinct elements wrapping the SAME coefficient objects (see _lone_coefficient_ntt)
             base = self.B.np_to_xfe(self.engine.download(out)[:, :share], res_field)
             X = self.B.ExtensionFieldElement
-            return [X(base[i % share].polynomial, res_field) for i in range(n)]
-        return self._from_device(out, kind, res_field, keep=True)
+            values = [X(base[i % share].polynomial, res_field) for i in range(n)]
+        else:
+            return self._from_device(out, kind, res_field, keep=True)
+        self.remember_planes(values, out)  # the values are the device's either way; only the identities differ
+        return values
 
     @staticmethod
     def _shared_output_period(arr, n):
@@ -265,15 +298,62 @@ class Glue:
         first = domain[0]
         if not coeffs:
             return [d.field.zero() for d in domain]
+        ck = "x" if self.B.is_xfe(coeffs[0]) else "b"
+        pk = "x" if self.B.is_xfe(first) else "b"
+        if ck == "x" and pk == "b" and self.B.is_bfe(first):
+            raise AttributeError("'BaseFieldElement' object has no attribute 'polynomial'")
+        if ck == "b" and pk == "x" and self.B.is_bfe(coeffs[0]):
+            raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
+        coset = self._as_coset(domain) if len(coeffs) <= len(domain) else None
+        if coset is not None:
+            # BASELINE config 3's structured case: the points are offset * omega^k, k < n, so the values are ONE
+            # coset transform (zero padding and the offset^j scale fused into the pass kernels) instead of
+            # n running-power evaluations of code/univariate.py:145-150
+            dc, ck, _ = self._to_device(coeffs)
+            self.coset_routed += 1
+            out = self.engine.ntt(dc, _ilog2(len(domain)), coset[1], offset=coset[0])
+            return self._from_device(out, "x" if pk == "x" else "b", first.field)
         dc, ck, _ = self._to_device(coeffs)
         dp, pk, pfield = self._to_device(domain)
-        if ck == "x" and pk == "b":
-            raise AttributeError("'BaseFieldElement' object has no attribute 'polynomial'")
-        if ck == "b" and pk == "x":
-            raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
         out = self.engine.eval_points(dc, dp)
         # value = point.field.zero() + c * xi ...: results carry the point's field (code/univariate.py:146-150)
         return self._from_device(out, "x" if pk == "x" else "b", pfield if pk == "x" else first.field)
+
+    def _as_coset(self, domain):
+        """(offset, omega) if `domain` is [offset * omega^k for k in range(n)] with n >= 2 a power of two, omega a
+        primitive n-th root of unity and every point in the base field (plain or lifted, all of one class and one
+        field object); else None"""
+        n = len(domain)
+        if n < 2 or n & (n - 1):
+            return None
+        first = domain[0]
+        if self.B.is_bfe(first):
+            cls, f = self.B.BaseFieldElement, first.field
+            if any(type(d) is not cls or d.field is not f for d in domain):
+                return None
+            v = [d.value for d in domain]
+        elif self.B.is_xfe(first):
+            cls, f = self.B.ExtensionFieldElement, first.field
+            v = []
+            for d in domain:
+                if type(d) is not cls or d.field is not f or len(d.polynomial.coefficients) > 1:
+                    return None
+                co = d.polynomial.coefficients
+                v.append(co[0].value if co else 0)
+        else:
+            return None
+        off = v[0]
+        if off == 0:
+            return None
+        w = v[1] * pow(off, P - 2, P) % P
+        if pow(w, n, P) != 1 or pow(w, n // 2, P) == 1:
+            return None
+        x = off
+        for k in range(n):
+            if v[k] != x:
+                return None
+            x = x * w % P
+        return off, w
 
     # ------------------------------------------------------------------ code/fri.py Domain
     def domain_evaluate(self, dom, polynomial):
@@ -345,12 +425,12 @@ class Glue:
         else:
             raise TypeError("cannot interpolate a column of %r" % type(first))
         omicron = table.omicron.value
-        buf = torch.zeros((len(cols) * pl, h + nr), dtype=torch.int64, device=eng.device)
+        buf = eng.zeros(len(cols) * pl, h + nr)
         f0 = buf[:, :h]
         if h > 1:
             eng.ntt(eng.upload(arr), _ilog2(h), omicron, inverse=True, out=f0)
         else:
-            f0.copy_(eng.upload(arr))
+            eng.upload_into(f0, arr)
         if nr:
             w = omega.value
             rho = [pow(w, 2 * k + 1, P) for k in range(nr)]
@@ -369,7 +449,13 @@ class Glue:
             # f = f0 - q + x^h * q touches coefficients [0, nr) and [h, h + nr) (overlapping when h < nr)
             pos = sorted(set(range(nr)) | set(range(h, h + nr)))
             where = {p_: i for i, p_ in enumerate(pos)}
-            fix = eng.download(buf[:, pos]).copy()
+            runs = []  # pos as contiguous column ranges [a, b)
+            for p_ in pos:
+                if runs and runs[-1][1] == p_:
+                    runs[-1][1] = p_ + 1
+                else:
+                    runs.append([p_, p_ + 1])
+            fix = np.concatenate([eng.download(buf[:, a:b]) for a, b in runs], axis=1)
             for ci in range(len(cols)):
                 at_rho = eng.download(eng.eval_points(f0[ci * pl:(ci + 1) * pl], pts))  # (pl, nr)
                 for s_ in range(pl):
@@ -380,7 +466,10 @@ class Glue:
                         row[where[i]] = (int(row[where[i]]) - q[i]) % P
                     for i in range(nr):
                         row[where[h + i]] = (int(row[where[h + i]]) + q[i]) % P
-            buf[:, pos] = eng.upload(fix)
+            at = 0
+            for a, b in runs:
+                eng.upload_into(buf[:, a:b], fix[:, at:at + b - a])
+                at += b - a
         return buf, pl, kind, first
 
     def table_interpolate_columns(self, table, omega, omega_order, column_indices, urandom):
@@ -474,16 +563,17 @@ class Glue:
             if ent is not None and ent[0] is codewords and len(ent[2]) == width and \
                     all(a is b for a, b in zip(ent[2], codewords)):
                 return ent[1]
-        cw = torch.empty((width, 3, N), dtype=torch.int64, device=eng.device)
-        host = [j for j in range(width) if self.planes_of(codewords[j]) is None or
-                self.planes_of(codewords[j]).shape[0] != 3]
+        cw = eng.alloc((width, 3, N))
         for j in range(width):
-            if j not in host:
-                cw[j].copy_(self.planes_of(codewords[j]))
-        if host:
-            planes = np.stack([self.B.xfe_to_np(codewords[j]) for j in host])
-            up = eng.upload(planes.reshape(3 * len(host), N)).reshape(len(host), 3, N)
-            cw[torch.tensor(host, device=eng.device)] = up
+            planes = self.planes_of(codewords[j])
+            lifted = self.lifted_planes_of(codewords[j]) if planes is None else None
+            if planes is not None and planes.shape[0] == 3:
+                eng.copy(cw[j], planes)
+            elif lifted is not None:  # a base-field codeword lifted element by element: c0 = the plane, c1 = c2 = 0
+                eng.copy(cw[j, 0:1], lifted)
+                eng.zero(cw[j, 1:3])
+            else:
+                eng.upload_into(cw[j], self.B.xfe_to_np(codewords[j]))
         if key is not None:
             self._kept[key] = (codewords, cw, list(codewords[:width]))
         return cw
@@ -638,7 +728,9 @@ class Glue:
         while npo2 < n:
             npo2 <<= 1
         tree.depth = _ilog2(npo2)  # code/salted_merkle.py:10-22 (0 leaves -> depth 0 as well)
-        tree.leafs = [(element, urandom(24)) for element in data_array]  # code/salted_merkle.py:25
+        from .marshal import bulk_allocation
+        with bulk_allocation():
+            tree.leafs = [(element, urandom(24)) for element in data_array]  # code/salted_merkle.py:25
         # code/salted_merkle.py:23: with no leaves the reference's own consistency assert fires
         assert n != 0, "in SaltedMerkle.__init__, next_power_of_two = 0 =/= 1 << self.depth = 1"
         nodes = self._row_tree(tree.leafs) if n == npo2 else None
@@ -698,8 +790,7 @@ class Glue:
         if planes is None or len(planes) != len(tpl.modes):
             return None
         eng = self.engine
-        salts = torch.from_numpy(np.frombuffer(b"".join(leaf[1] for leaf in leafs), dtype=np.uint8)
-                                 .reshape(n, len(salt0)).copy()).to(eng.device)
+        salts = eng.upload_bytes(np.frombuffer(b"".join(leaf[1] for leaf in leafs), dtype=np.uint8).reshape(n, len(salt0)))
         # a couple of rows rendered on the host as well: the template must reproduce the caller's pickler
         for i in {0, n // 2, n - 1}:
             t = tpl if marshal.row_signature(self.B, rows[i]) == tpl.signature else marshal.row_template(self.B, rows[i])
@@ -712,7 +803,7 @@ class Glue:
             t = marshal.row_template(self.B, rows[int(exc[0])])
             if t is None or shapes > self.MAX_ROW_SHAPES:
                 return None
-            todo = torch.from_numpy(np.sort(exc).astype(np.int32)).to(eng.device)
+            todo = eng.upload_bytes(np.sort(exc).astype(np.uint32).view(np.uint8)).view(torch.int32)
             nodes, rest = eng.merkle_rows(planes, t.modes, t.tpl, t.seg_off, n, salts, frame[0], frame[1], rows=todo,
                                           nodes=nodes, build_upper=False)
             if len(rest) == len(exc):

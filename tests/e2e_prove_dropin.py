@@ -12,7 +12,6 @@ which an unmodified prove() keeps."""
 import hashlib
 import json
 import os
-import random
 import sys
 import time
 
@@ -38,8 +37,8 @@ def main(backend="fake", out=None, source="++++", inputs="", golden_name="bfs.js
         from stark_brainfuck_b200 import Engine
         engine = Engine(0)
     glue = dropin.install(REFERENCE_DIR, engine=engine)
-    R = random.Random(1234)
-    fake = lambda n: bytes(R.getrandbits(8) for _ in range(n))  # noqa: E731
+    from trace_backend import SeededUrandom
+    fake = SeededUrandom(1234)  # the byte stream of bytes(random.Random(1234).getrandbits(8) for ...), generated in bulk
     os.urandom = fake
     import salted_merkle
     salted_merkle.urandom = fake

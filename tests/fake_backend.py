@@ -19,7 +19,15 @@ def _addr(p):
         return 0
     if isinstance(p, int):
         return p
-    return p.value or 0
+    if hasattr(p, "_obj"):  # byref(x)
+        return C.addressof(p._obj)
+    if isinstance(p, C.c_void_p):
+        return p.value or 0
+    return C.cast(p, C.c_void_p).value or 0
+
+
+def _set_i32(p, v):
+    C.c_int32.from_address(_addr(p)).value = int(v)
 
 
 def _u64(addr, count):
@@ -131,7 +139,7 @@ class FakeLib:
                              bytes(_u8(_addr(h_suf), suf_len)) if suf_len else b"", rows)
         if len(exc):
             np.ctypeslib.as_array((C.c_uint32 * len(exc)).from_address(_addr(h_exc)))[:] = exc
-        h_n_exc._obj.value = len(exc)
+        _set_i32(h_n_exc, len(exc))
         if build_upper and not len(exc) and n > 1:
             nodes[:] = orc.merkle_upper(nodes.copy())
         return 0
@@ -185,7 +193,7 @@ class FakeLib:
         out, flag = orc.quotients(cw, shift, off, coeffs, fac, kind, height, oinv, offset, omega)
         if nc:
             _u64(_addr(d_out), nc * 3 * N).reshape(nc, 3, N)[:] = out
-        h_flag._obj.value = int(flag)
+        _set_i32(h_flag, flag)
         return 0
 
     def b2s_open_multi(self, h_planes, h_strides, n_planes, h_nodes, h_npo2, h_counts, h_indices, n_sets, h_values,

@@ -139,6 +139,26 @@ def case_coset_and_poly(env):
     assert bdig(poly.evaluate_domain(rand_bfe_list(env, 703, 50))) == S["evaluate_domain_bfe"]["digest"]
     assert xdig(xpoly.evaluate_domain(rand_xfe_list(env, 704, 41))) == S["evaluate_domain_xfe"]["digest"]
     assert poly.evaluate_domain([]) == []
+    # structured domains (BASELINE config 3): points offset * omega^k are routed to ONE coset transform; the values
+    # are the reference's (golden) and those of the generic running-power path on the same points in another order
+    w64 = env.xfield.lift(env.field.primitive_nth_root(64))
+    cos = [env.xfield.lift(env.field.generator()) * (w64 ^ i) for i in range(64)]
+    xp64 = env.Polynomial(rand_xfe_list(env, 705, 64))
+    g = getattr(env, "glue", None)
+    before = g.coset_routed if g is not None else 0
+    on_coset = xp64.evaluate_domain(cos)
+    assert xdig(on_coset) == S["evaluate_domain_xfe_coset64"]["digest"]
+    assert all(v.field is env.xfield for v in on_coset) and pickle.dumps(on_coset[3]) == pickle.dumps(xp64.evaluate(cos[3]))
+    swapped = [cos[1], cos[0]] + cos[2:]  # not a coset in this order: generic path
+    assert triples(xp64.evaluate_domain(swapped)) == triples([on_coset[1], on_coset[0]] + on_coset[2:])
+    rotated = cos[5:] + cos[:5]  # the coset of offset * omega^5
+    assert triples(xp64.evaluate_domain(rotated)) == triples(on_coset[5:] + on_coset[:5])
+    bcos = [env.field.generator() * (env.field.primitive_nth_root(64) ^ i) for i in range(64)]
+    assert vals(poly.evaluate_domain(bcos)) == [poly.evaluate(b).value for b in bcos]
+    short = env.Polynomial(rand_bfe_list(env, 706, 100))  # more coefficients than points: generic path
+    assert vals(short.evaluate_domain(bcos[:2])) == [short.evaluate(b).value for b in bcos[:2]]
+    if g is not None:
+        assert g.coset_routed == before + 3
     # fast_multiply rides on the patched ntt/intt (code/ntt.py:45-79)
     a = env.Polynomial(rand_bfe_list(env, 31, 20))
     b = env.Polynomial(rand_bfe_list(env, 32, 25))

@@ -439,3 +439,110 @@ def test_open_multi_matches_single_calls(eng):
     from stark_brainfuck_b200._lib import B2SError
     with pytest.raises(B2SError):
         eng.open_multi([(None, trees[1][1], [1 << 7])])
+
+
+def _planes(seed, n, ext):
+    return rand_xfe(seed, n) if ext else rand_bfe(seed, n).reshape(1, n)
+
+
+def _lift(a):
+    out = np.zeros((3, a.shape[1]), dtype=np.uint64)
+    out[:a.shape[0]] = a
+    return out
+
+
+@pytest.mark.parametrize("m", (65, 300, 4096))
+@pytest.mark.parametrize("k", (1, 50, 1 << 10))
+def test_eval_points_multi_chunk_vs_oracle(eng, m, k):
+    """b2s_eval_points beyond one chunk of coefficients (m > 64), all four plane combinations
+    (code/univariate.py:145-154; Glue._interpolated_planes depends on this branch for every table of height >= 128)"""
+    for cx in (False, True):
+        for px in (False, True):
+            c, pts = _planes(900 + m, m, cx), _planes(901 + k, k, px)
+            got = eng.download(eng.eval_points(eng.upload(c), eng.upload(pts)))
+            if not cx and not px:
+                want = orc.eval_points(c[0], pts[0]).reshape(1, k)
+            else:
+                want = orc.eval_points(_lift(c), _lift(pts))
+            assert np.array_equal(got, want), (m, k, cx, px)
+
+
+def test_eval_points_config3_sizes(eng):
+    """BASELINE config 3: 2^18 extension-field coefficients.  At 50 arbitrary points against the oracle; at 2^10
+    points of the coset 7 * omega^k against the coset transform (itself pinned to the oracle and the goldens)."""
+    logm = 18
+    m = 1 << logm
+    c = rand_xfe(118, m)
+    dc = eng.upload(c)
+    pts = rand_xfe(119, 50)
+    assert np.array_equal(eng.download(eng.eval_points(dc, eng.upload(pts))), orc.eval_points(c, pts))
+    w = root_of_unity(logm)
+    cos = np.array([7 * pow(w, i, P) % P for i in range(1 << 10)], dtype=np.uint64)
+    full = eng.download(eng.ntt(dc, logm, w, offset=7))
+    assert np.array_equal(eng.download(eng.eval_points(dc, eng.upload(cos))), full[:, :1 << 10])
+    b = rand_bfe(120, m)
+    bpts = rand_bfe(121, 1 << 10)
+    assert np.array_equal(eng.download(eng.eval_points(eng.upload(b), eng.upload(bpts)))[0], orc.eval_points(b, bpts))
+
+
+@pytest.mark.parametrize("logn", (12, 20))
+def test_scale_big_vs_oracle(eng, logn):
+    """b2s_scale at 2^12 and 2^20 coefficients, base-field and extension-field factor (code/univariate.py:168-169)"""
+    n = 1 << logn
+    c = rand_bfe(930 + logn, n)
+    f = 0x123456789ABCDEF % P
+    assert np.array_equal(eng.download(eng.scale(eng.upload(c), f))[0], orc.scale(f, c))
+    xc = rand_xfe(931 + logn, n)
+    xf = [int(v) for v in rand_xfe(932, 1)[:, 0]]
+    assert np.array_equal(eng.download(eng.scale(eng.upload(xc), xf)), orc.xscale(xf, xc))
+
+
+def test_row_leaves_vs_oracle(eng):
+    """b2s_merkle_rows (zipped, salted rows; code/salted_merkle.py:25-35) against orc_row_leaves on a synthetic
+    template: every integer width, trimmed shapes reported as exceptions, the row-list pass, the inner nodes."""
+    import torch
+    n = 1 << 11
+    R = random.Random(77)
+    edge = [0, 1, 255, 256, 65535, 65536, (1 << 31) - 1, 1 << 31, (1 << 32) - 1, 1 << 39, (1 << 63) - 1, 1 << 63, P - 1]
+    planes = [np.array([R.choice(edge) if R.random() < 0.4 else R.randrange(P) for _ in range(n)], dtype=np.uint64)
+              for _ in range(7)]
+    planes[3][planes[3] == 0] = 1
+    planes[3][5] = planes[3][900] = 0  # mode 1 violated: exceptions
+    planes[6][:] = 0                   # mode 2 plane
+    planes[6][77] = 9                  # ... violated
+    modes = np.array([0, 0, 0, 1, 0, 0, 2], dtype=np.uint8)
+    segs = [bytes(R.getrandbits(8) for _ in range(L)) for L in (140, 3, 0, 17, 250, 1, 33)]
+    tpl = b"".join(segs)
+    seg_off = np.cumsum([0] + [len(x) for x in segs]).astype(np.uint32)
+    salts = np.array([[R.getrandbits(8) for _ in range(24)] for _ in range(n)], dtype=np.uint8)
+    pre, suf = b"\x80\x04\x95\x1c\0\0\0\0\0\0\0C\x18", b"\x94."
+    want = np.zeros((2 * n, 64), dtype=np.uint8)
+    exc_want = orc.row_leaves(planes, modes, tpl, seg_off, n, want, salts, pre, suf)
+    assert sorted(exc_want.tolist()) == [5, 77, 900]
+    dev = [eng.upload(a)[0] for a in planes]
+    d_salts = eng.upload_bytes(salts)
+    nodes, exc = eng.merkle_rows(dev, modes, tpl, seg_off, n, d_salts, pre, suf)
+    assert sorted(exc.tolist()) == [5, 77, 900]
+    got = np.frombuffer(eng.download_bytes(nodes), dtype=np.uint8).reshape(2 * n, 64)
+    ok = np.ones(n, dtype=bool)
+    ok[[5, 77, 900]] = False
+    assert np.array_equal(got[n:][ok], want[n:][ok])
+    # second pass over the exception rows with a template of their shape (here: every plane emitted, no checks)
+    modes2 = np.zeros(7, dtype=np.uint8)
+    segs2 = segs + [b"xyz"]
+    tpl2, seg2 = b"".join(segs2), np.cumsum([0] + [len(x) for x in segs2]).astype(np.uint32)
+    rows = np.array([5, 77, 900], dtype=np.uint32)
+    orc.row_leaves(planes, modes2, tpl2, seg2, n, want, salts, pre, suf, rows=rows)
+    d_rows = eng.upload_bytes(rows.view(np.uint8)).view(torch.int32)
+    nodes, exc = eng.merkle_rows(dev, modes2, tpl2, seg2, n, d_salts, pre, suf, rows=d_rows, nodes=nodes, build_upper=False)
+    assert len(exc) == 0
+    eng.merkle_upper(nodes)
+    want = orc.merkle_upper(want)
+    got = np.frombuffer(eng.download_bytes(nodes), dtype=np.uint8).reshape(2 * n, 64)
+    assert np.array_equal(got[1:], want[1:])
+    # unsalted rows, one leaf
+    one = [a[:1].copy() for a in planes[:6]]
+    w1 = np.zeros((2, 64), dtype=np.uint8)
+    orc.row_leaves(one, modes2[:6], tpl, seg_off, 1, w1)
+    n1, _ = eng.merkle_rows([eng.upload(a)[0] for a in one], modes2[:6], tpl, seg_off, 1)
+    assert eng.download_bytes(n1)[64:] == w1[1:].tobytes()

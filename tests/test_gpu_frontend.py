@@ -26,7 +26,8 @@ def test_ntt_quirks(env):
     fc.case_ntt_quirks(env)
 
 
-def test_coset_and_poly(env):
+def test_coset_and_poly(env, mirror_gpu):
+    env.glue = mirror_gpu.glue()
     fc.case_coset_and_poly(env)
 
 

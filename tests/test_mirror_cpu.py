@@ -19,7 +19,8 @@ def test_ntt_quirks(env):
     fc.case_ntt_quirks(env)
 
 
-def test_coset_and_poly(env):
+def test_coset_and_poly(env, mirror_cpu):
+    env.glue = mirror_cpu.glue()
     fc.case_coset_and_poly(env)
 
 
