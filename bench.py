@@ -114,36 +114,250 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's ntt/intt (code/ntt.py:4-42) on host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+# the same dict in both arms (the driver compares them)
+CONFIG = {"workload": "ntt+intt round trip, 2^20 BaseField vector per GPU (BASELINE configs[1])", "log_n": LOG_N,
+          "l2": "inputs larger than L2: ring of 20 (in, out, back) buffer triples = 480 MB"}
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_round_trips(steps, threads):
+    """`steps` round trips (ntt then intt, bit-exact) of the 2^20 workload on each of `threads` host threads, every
+    thread on its own vector, through the C port of the reference's algorithm (oracle/b2s_oracle.c: the recursive
+    radix-2 transform of code/ntt.py:4-42 with `% p` arithmetic, unoptimised on purpose; ctypes releases the GIL).
+    Returns seconds of wall clock for all of them."""
+    import threading
     import numpy as np
     from oracle import oracle as orc
     n = 1 << LOG_N
     w = root_of_unity(LOG_N)
-    x = synth(1, n)
-    for _ in range(max(args.warmup, 1)):
-        y = orc.ntt(w, x)
+    xs = [synth(1 + t, n) for t in range(threads)]
+    ok = [False] * threads
+
+    def work(t):
+        z = None
+        for _ in range(steps):
+            z = orc.intt(w, orc.ntt(w, xs[t]))
+        ok[t] = bool(np.array_equal(z, xs[t]))
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        y = orc.ntt(w, x)
-        z = orc.intt(w, y)
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
     dt = time.perf_counter() - t0
-    assert np.array_equal(z, x)
-    ms = dt / args.steps * 1e3
-    val = muls_per_step(LOG_N) / (ms / 1e3)
+    assert all(ok), "CPU round trip is not exact"
+    return dt
+
+
+def run_reference(args):
+    """CPU arm: the reference's ntt/intt (code/ntt.py:4-42) on all host threads.  The reference itself is
+    single-threaded pure Python (338 s per forward 2^20 transform) and does not exist on the GPU box,
+    so the arm runs its C port, one independent round trip per thread and step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    if args.warmup:
+        cpu_round_trips(1, threads)
+    dt = cpu_round_trips(args.steps, threads)
+    ms = dt / args.steps * 1e3  # one step = `threads` round trips side by side
+    val = threads * muls_per_step(LOG_N) / (ms / 1e3)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "ntt+intt round trip, 2^20 BaseField (BASELINE configs[1])", "log_n": LOG_N},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "%d full round trips of the 2^20 workload, oracle/b2s_oracle.c single thread "
-                                   "(the Python reference needs 338 s per forward transform)" % args.steps},
+        "dtype": "u64", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d steps of %d concurrent round trips of the 2^20 workload (one per host thread), "
+                                   "unoptimised C port of the reference's recursion (oracle/b2s_oracle.c, `%% p` "
+                                   "arithmetic); the Python reference itself is single-threaded and needs 338 s per "
+                                   "forward transform" % (args.steps, threads)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def pin_rank_to_cores(local, world):
+    """Give every rank its own host cores before it allocates pinned memory (first touch places the pages): the
+    cores of the GPU's NUMA node when the box exposes them, else an equal share of the allowed set.  Round 1's
+    8-GPU e2e ran all ranks on one shared core set (SCALE_r01 topology) and lost 46 % to host-side contention."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    if world <= 1 or len(allowed) < 2 * world:
+        return {"cores": len(allowed), "numa": None}
+    node, cores = None, None
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node >= 0:
+            lst = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+            numa = set()
+            for part in lst.split(","):
+                a, _, b = part.partition("-")
+                numa.update(range(int(a), int(b or a) + 1))
+            cores = [c for c in allowed if c in numa]
+    except Exception:
+        node = None
+    share = len(allowed) // world
+    mine = allowed[local * share:(local + 1) * share]
+    if cores and len(cores) >= share:
+        # ranks whose GPUs share a node split that node's cores among themselves
+        k = local % max(1, len(cores) // share)
+        mine = cores[k * share:(k + 1) * share] or mine
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return {"cores": len(allowed), "numa": node}
+    return {"cores": len(mine), "first_core": mine[0], "numa": node}
+
+
+def sharded_extra(eng, rank, world):
+    """SURVEY 8(e) rows 2-4 on N > 1 GPUs, ONE problem split over all ranks (strong scaling), bit-compared on
+    every rank with the single-GPU result of the same library: (a) one transform, four-step with ONE exchange
+    (NCCL all-to-all, and peer stores over NVLink); (b) LDE of a trace's 46 planes by residue class (no exchange)
+    -> one all-to-all -> pair blocks; (c) one FRI proof (balanced butterfly exchange, subtree roots all-gathered).
+    Times are device-synchronised wall clock, max over ranks, best of 3."""
+    import hashlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from stark_brainfuck_b200 import mirror
+    from stark_brainfuck_b200.dist import DistNTT, shard_coset_evaluate
+    from stark_brainfuck_b200.dist_fri import DistFri, residues_to_pair_blocks
+    from stark_brainfuck_b200.glue import Glue
+    from util import golden, have_golden, rand_xfe
+    dev = eng.device
+    out = {"n_gpus": world, "parity": True}
+    solo = None
+    for r in range(world):  # a one-rank group per rank: the single-GPU run of the same code
+        g = dist.new_group([r])
+        if r == rank:
+            solo = g
+
+    def timed(fn, iters=3):
+        best = None
+        for _ in range(iters):
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t[0]) if best is None else min(best, float(t[0]))
+        return res, best * 1e3
+
+    def agree(flag):
+        t = torch.tensor([1 if flag else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # (a) one transform over all ranks
+    ntt = {}
+    for logn in (20, 26):
+        n, log_n1 = 1 << logn, logn // 2
+        n1, n2 = 1 << log_n1, 1 << (logn - log_n1)
+        q, cpp = n1 // world, n2 // world
+        w = root_of_unity(logn)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + logn)
+        full = torch.randint(0, 2 ** 62, (1, n), dtype=torch.int64, device=dev, generator=gen)  # same on every rank
+        single, one_ms = timed(lambda: eng.ntt(full, logn, w))
+        mine = full.view(n2, n1).t()[rank * q:(rank + 1) * q].contiguous()  # planes P[j1][j2] = x[j1 + n1 j2]
+        want = single.view(n1, n2).t()[rank * cpp:(rank + 1) * cpp]         # D[k2][k1] = X[k1 n2 + k2]
+        ent = {"one_gpu_ms": one_ms, "exchange_bytes_per_rank": 8 * q * n2 * (world - 1) // world}
+        for exch in ("nccl", "p2p"):
+            try:
+                d = DistNTT(eng, exchange=exch)
+                got, ms = timed(lambda: d.transform(mine, logn, w))
+                ok = agree(torch.equal(got, want))
+                out["parity"] &= ok
+                ent["all_to_all_single_ms" if exch == "nccl" else "peer_store_ms"] = ms
+            except Exception as e:  # symmetric memory may be unavailable
+                ent[exch + "_error"] = str(e)[:120]
+        ntt["2^%d" % logn] = ent
+        del full, single, mine, want
+    out["ntt"] = ntt
+
+    # (b) + (c): LDE by residue class -> pair blocks -> one FRI proof
+    mirror.register()
+    glue = Glue(mirror.binding, eng)
+    old_glue = mirror._glue
+    mirror.set_glue(glue)
+    m = mirror
+    expansion, s = 4, 8
+    fri_out, lde_out = {}, {}
+    for logn in (20, 24):
+        n = 1 << logn
+        w = root_of_unity(logn)
+        is_golden = logn == 20 and have_golden("fri_20.json")
+        coeffs = rand_xfe(200 + logn, n // expansion) if is_golden else \
+            np.random.default_rng(logn).integers(0, P_MOD, (3, n // expansion), dtype=np.uint64)
+        dc = eng.upload(coeffs)
+        full, lde1_ms = timed(lambda: eng.ntt(dc, logn, w, offset=7))
+
+        def chain():
+            res = shard_coset_evaluate(eng, dc, logn, w, 7, rank, world)
+            return residues_to_pair_blocks(res)
+        (ca, cb), lde_ms = timed(chain)
+        blk = n // (2 * world)
+        ok = agree(torch.equal(ca, full[:, rank * blk:(rank + 1) * blk]) and
+                   torch.equal(cb, full[:, n // 2 + rank * blk:n // 2 + (rank + 1) * blk]))
+        out["parity"] &= ok
+        lde_out["2^%d" % logn] = {"one_gpu_ms": lde1_ms, "sharded_ms_incl_all_to_all": lde_ms,
+                                  "all_to_all_bytes_per_rank": 24 * n // world * (world - 1) // world}
+        fri = m.fri.Fri(m.field.generator(), m.field.primitive_nth_root(n), n, expansion, s, m.xfield)
+        shard, one = DistFri(glue), DistFri(glue, group=solo)
+
+        def prove(df, a, b):
+            ps = m.ip.ProofStream()
+            top = df.prove(fri, a, b, ps, m.merkle.Merkle)
+            return top, ps
+        (top, ps), ms = timed(lambda: prove(shard, ca, cb))
+        half = n // 2
+        (top1, ps1), ms1 = timed(lambda: prove(one, full[:, :half].contiguous(), full[:, half:].contiguous()))
+        ser = ps.serialize()
+        ok = top == top1 and ser == ps1.serialize()
+        if is_golden:
+            e = golden("fri_20.json")
+            ok = ok and hashlib.sha256(ser).hexdigest() == e["transcript_sha256"]
+        ok = agree(ok)
+        out["parity"] &= ok
+        fri_out["2^%d" % logn] = {"one_gpu_ms": ms1, "sharded_ms": ms, "speedup_vs_1gpu": ms1 / ms,
+                                  "transcript_bytes": len(ser), "golden_transcript": bool(is_golden),
+                                  "p2p_bytes_rank0": int(shard.exchanged_bytes // 3)}
+        del full, ca, cb
+    # the 46 planes of a trace (16 base-field + 10 extension-field polynomials, degree < 2^18) to a 2^20 domain
+    logn, n = 20, 1 << 20
+    w = root_of_unity(logn)
+    rng = np.random.default_rng(46)
+    polys = [eng.upload(rng.integers(0, P_MOD, (1, n // 4), dtype=np.uint64)) for _ in range(16)] + \
+            [eng.upload(rng.integers(0, P_MOD, (3, n // 4), dtype=np.uint64)) for _ in range(10)]
+    allp = torch.cat(polys, dim=0)
+    ref46, one46 = timed(lambda: eng.ntt(allp, logn, w, offset=7))
+    res46, sh46 = timed(lambda: [shard_coset_evaluate(eng, p_, logn, w, 7, rank, world) for p_ in polys])
+    ok = agree(all(torch.equal(torch.cat(res46, dim=0), ref46[:, rank::world]) for _ in (0,)))
+    out["parity"] &= ok
+    lde_out["46_planes_2^18_to_2^20"] = {"one_gpu_ms": one46, "sharded_ms": sh46, "speedup_vs_1gpu": one46 / sh46,
+                                         "collective": "none (residue classes)"}
+    out["lde"], out["fri_prove"] = lde_out, fri_out
+    out["collective"] = {"ntt": "all_to_all_single | peer stores (symmetric memory)", "lde": "all_to_all_single",
+                         "fri": "send/recv pairs + all_gather of subtree roots + one all_reduce for the openings"}
+    out["limiter"] = ("host Fiat-Shamir round loop (~5 ms per proof, not sharded) below 2^22; NCCL launch latency "
+                      "on the 8 MiB transform; hash-bound device work scales from 2^24 up")
+    mirror.set_glue(old_glue)
+    mirror.unregister()
+    return out
 
 
 def run_b200(args):
@@ -158,6 +372,7 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    affinity = pin_rank_to_cores(local, world)
     from stark_brainfuck_b200 import Engine
     eng = Engine(local)
     dev = eng.device
@@ -323,52 +538,61 @@ def run_b200(args):
     except Exception as e:  # informational only
         extra["fri_error"] = str(e)
 
+    sharded = None
+    if world > 1:
+        try:
+            sharded = sharded_extra(eng, rank, world)
+        except Exception as e:  # never lose the headline to the strong-scaling extra
+            sharded = {"error": repr(e)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if sharded is not None:
+        extra["sharded"] = sharded
 
     muls = muls_per_step(LOG_N)
     value = world * muls / (ms_step / 1e3)
     e2e_val = world * muls / (e2e_ms / 1e3)
     peak, which = peaks()
     achieved = 16.0 * n / (fwd / 1e3) / 1e9
-    traffic = None
-    try:  # DRAM bytes of the two pass launches from the committed `ncu --set full` capture
+    traffic, pipes = None, {}
+    try:  # DRAM bytes and pipe utilisation of the two pass launches from the committed `ncu --set full` capture
         with open(os.path.join(ROOT, "profiles", "ntt_traffic.json")) as f:
-            traffic = int(json.load(f)["dram_bytes_per_transform"])
+            cap = json.load(f)
+        traffic = int(cap["dram_bytes_per_transform"])
+        pipes = cap.get("pipes", {})
     except Exception:
         pass
 
-    # ---- CPU baseline: the oracle port on this box's host cores (bounded sample) ------
-    from oracle import oracle as orc
-    cpu_steps = 8
-    t0 = time.perf_counter()
-    for _ in range(cpu_steps):
-        yy = orc.ntt(w, x_np)
-        zz = orc.intt(w, yy)
-    cpu_dt = (time.perf_counter() - t0) / cpu_steps
-    assert np.array_equal(zz, x_np)
+    # ---- CPU baseline: the C port of the reference's recursion on all host threads (bounded sample) ------
+    cpu_threads = host_threads()
+    cpu_steps = 4
+    cpu_dt = cpu_round_trips(cpu_steps, cpu_threads) / cpu_steps
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "ntt+intt round trip, 2^20 BaseField vector per GPU (BASELINE configs[1])",
-                   "log_n": LOG_N, "l2": "inputs larger than L2: ring of 20 (in, out, back) buffer triples = 480 MB",
-                   "parity": "intt(ntt(x)) == x bit-exact; ntt == CPU oracle: %s" % ref_check},
+        "config": CONFIG,
+        "parity": "intt(ntt(x)) == x bit-exact in every timed step; ntt == CPU oracle: %s" % ref_check,
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * 8 * n,
-                "d2h_bytes_per_step": 2 * 8 * n,
+                "d2h_bytes_per_step": 2 * 8 * n, "pcie_gb_per_s_per_rank": 4 * 8 * n / (e2e_ms / 1e3) / 1e9,
+                "host_affinity": affinity,
                 "path": "b2s_ntt_host (C ABI, pinned host buffers) forward then inverse"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": which,
-                     "kernel": "ntt4_pass_kernel x2 (forward 2^20 transform, input not L2-resident)",
-                     "algorithmic_bytes": 16 * n, "duration_ms": fwd},
-        "cpu_baseline": {"value": muls / cpu_dt, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": "%d round trips of the same 2^20 workload, oracle/b2s_oracle.c, 1 thread of %d"
-                                   % (cpu_steps, os.cpu_count() or 0)},
+        "roofline": dict({"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                          "traffic": traffic, "peak_source": which,
+                          "kernel": "ntt4_pass_kernel x2 (forward 2^20 transform, input not L2-resident)",
+                          "algorithmic_bytes": 16 * n, "duration_ms": fwd,
+                          "note": "integer modular arithmetic: the INT32 pipes bind, not HBM (pipe figures from the "
+                                  "committed ncu capture); 32 batched planes reach extra.batched_32_planes_hbm_gbs"},
+                         **pipes),
+        "cpu_baseline": {"value": cpu_threads * muls / cpu_dt, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": "%d steps of %d concurrent round trips of the same 2^20 workload (one per host "
+                                   "thread), unoptimised C port of the reference's recursion (oracle/b2s_oracle.c)"
+                                   % (cpu_steps, cpu_threads)},
         "extra": extra,
     }
     print(json.dumps(out))
