@@ -65,6 +65,10 @@ const char *b2s_last_error(void);
  * Fails (B2S_ERR_CUDA) when no sm_100 device is visible: there is no CPU fallback. */
 int b2s_init(int device);
 int b2s_shutdown(void);
+/* Return cached device memory to the driver: the stream-ordered scratch pool (which otherwise keeps up to 2 GiB
+ * of freed scratch for reuse) and the twiddle-table cache.  Synchronises the device.  For callers that share the
+ * device with another allocator and run into its out-of-memory condition. */
+int b2s_trim(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t b2s_launch_count(void);
 int b2s_device_sm_count(void);
@@ -186,14 +190,17 @@ int b2s_gather(const uint64_t *d_planes, uint64_t plane_stride, uint32_t n_plane
  * factors h_factors[m * max_factors + f] = (variable << 8) | exponent, exponent 0 = unused.
  * d_out: n_constraints codewords in the same plane layout.  *h_zero_flag is set to 1 when a
  * zerofier vanishes on the domain (the reference's batch_inverse asserts, code/ntt.py:178-179).
- * Synchronises. */
+ * h_base_columns (HOST, `width` bytes, or NULL): non-zero for a codeword the caller KNOWS to be a lifted
+ * base-field column, i.e. with all-zero planes 1 and 2 (every Table.extend of the reference lifts its base
+ * codewords, e.g. code/io_table.py:106-107); their factors are multiplied in the base field (1 multiplication
+ * instead of 9).  NULL: the library scans the columns itself.  Synchronises. */
 #define B2S_ZEROFIER_BOUNDARY 1
 #define B2S_ZEROFIER_TRANSITION 2
 #define B2S_ZEROFIER_TERMINAL 3
 int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, uint64_t shift, uint32_t n_constraints,
                   const uint32_t *h_mono_off, const uint64_t *h_coeffs, const uint32_t *h_factors, uint32_t max_factors,
                   uint32_t zerofier_kind, uint64_t height, uint64_t omicron_inv, uint64_t offset, uint64_t omega,
-                  uint64_t *d_out, int *h_zero_flag, void *stream);
+                  uint64_t *d_out, int *h_zero_flag, const uint8_t *h_base_columns, void *stream);
 
 /* code/fri.py:141-176, the query phase: the codeword elements (`tree.leafs[i]`, :150/:169) and authentication
  * paths (`tree.open(i)`, code/merkle.py:46-52) of SEVERAL trees in one launch and one synchronisation.  Set s

@@ -55,16 +55,20 @@ def main():
         eng.merkle_field(rcw, tpl)
         eng.merkle_field(ext_cw[0][:3], tpl)
         mark("2 trees (stand-ins for the salted ones)")
-        quotients = []
-        for t, bc, xc, pr in zip(tables, base_cw, ext_cw, progs):
+        quotients, assembled = [], []
+        for t, bc, xc in zip(tables, base_cw, ext_cw):
             W = t["full_width"]
             cw = torch.zeros((W, 3, N), dtype=torch.int64, device=eng.device)
             cw[:t["base_width"], 0] = bc  # lifted base columns (code/processor_table.py:421)
             cw[t["base_width"]:] = xc.reshape(-1, 3, N)
+            assembled.append(cw)
+        mark("table planes assembled (lifted base columns + extension columns)")
+        for t, cw, pr in zip(tables, assembled, progs):
+            flags = [j < t["base_width"] for j in range(t["full_width"])]  # what Glue._table_planes knows
             for kind in (1, 2, 3):
-                out, _ = eng.quotients(cw, N // h, *pr[kind - 1], kind, h, oinv, 7, w)
+                out, _ = eng.quotients(cw, N // h, *pr[kind - 1], kind, h, oinv, 7, w, base_columns=flags)
                 quotients.append(out)
-        mark("quotients (47 constraints, 5 tables)")
+        mark("quotients (47 constraints, 5 tables, 15 calls)")
         cols = [rcw] + [b[i:i + 1] for b in base_cw for i in range(b.shape[0])]
         cols += [x[3 * i:3 * i + 3] for x in ext_cw for i in range(x.shape[0] // 3)]
         cols += [q[i] for q in quotients for i in range(q.shape[0])]

@@ -33,6 +33,7 @@ SIGNATURES = {
     "b2s_last_error": (C.c_char_p, []),
     "b2s_init": (_int, [_int]),
     "b2s_shutdown": (_int, []),
+    "b2s_trim": (_int, []),
     "b2s_launch_count": (_u64, []),
     "b2s_device_sm_count": (_int, []),
     "b2s_gl_mul": (_u64, [_u64, _u64]),
@@ -51,7 +52,7 @@ SIGNATURES = {
     "b2s_fri_fold": (_int, [_vp, _u64, _u64, C.POINTER(_u64), _u64, _u64, _vp, _u64, _TP, _vp, _vp]),
     "b2s_gather": (_int, [_vp, _u64, _u32, _vp, _u32, _vp, _vp]),
     "b2s_quotients": (_int, [_vp, _u64, _u32, _u64, _u32, _vp, _vp, _vp, _u32, _u32, _u64, _u64, _u64, _u64, _vp,
-                             C.POINTER(C.c_int), _vp]),
+                             C.POINTER(C.c_int), _vp, _vp]),
     "b2s_open_multi": (_int, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp]),
     "b2s_combination": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _u32, _u64, _u64, _u64, _vp, _u64, _vp]),
     "b2s_dist_twiddle_transpose": (_int, [_vp, _u64, _u32, _u32, _u64, _u64, _u64, C.POINTER(_vp), _u32, _u64, _u64,

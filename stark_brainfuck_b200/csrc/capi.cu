@@ -44,11 +44,25 @@ extern "C" int b2s_init(int device) {
         return B2S_ERR_CUDA;
     }
     g_sm_count = prop.multiProcessorCount;
-    // keep freed scratch in the stream-ordered pool instead of returning it to the driver
+    // Keep freed scratch (the transform's work buffer, gather buffers) in the stream-ordered pool instead of
+    // returning it to the driver at every synchronisation -- up to a bound: the caller's own allocator (torch's
+    // caching allocator uses cudaMalloc) shares the device, and what this pool holds back it cannot use.
+    // b2s_trim() returns everything.
     cudaMemPool_t pool;
     B2S_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thresh = UINT64_MAX;
+    uint64_t thresh = (uint64_t)2 << 30;
     B2S_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    return 0;
+}
+
+extern "C" int b2s_trim(void) {
+    int device = 0;
+    B2S_CUDA(cudaGetDevice(&device));
+    B2S_CUDA(cudaDeviceSynchronize());
+    cudaMemPool_t pool;
+    B2S_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    B2S_CUDA(cudaMemPoolTrimTo(pool, 0));
+    ntt_cache_clear();
     return 0;
 }
 

@@ -14,6 +14,7 @@
 // compulsory read of the input and write of the output.  Twiddle tables are built once per
 // (root, size) on the device, cached for the life of the library and staged into shared memory
 // by TMA bulk copies.
+#include <atomic>
 #include <map>
 #include <mutex>
 
@@ -133,7 +134,10 @@ struct TabKey {
     }
 };
 std::mutex g_tab_mu;
-std::map<TabKey, TabEntry> g_tab;  // built once per (base, size, layout, device), kept until shutdown
+std::map<TabKey, TabEntry> g_tab;  // built once per (base, size, layout, device)
+std::atomic<u64> g_tab_generation{0};  // bumped whenever the tables are dropped: cached plans of older generations are stale
+size_t g_tab_bytes = 0;            // ... and bounded: callers with ever-changing roots or coset offsets
+constexpr size_t TAB_BUDGET_BYTES = (size_t)256 << 20;
 
 int get_table(const Tab4 &t, cudaStream_t st, const u64 **out) {
     std::lock_guard<std::mutex> lk(g_tab_mu);
@@ -145,7 +149,16 @@ int get_table(const Tab4 &t, cudaStream_t st, const u64 **out) {
         TabEntry e;
         const u32 cnt = 1u << t.log_count;
         const u32 alloc = cnt < 2 ? 2 : cnt;
+        if (g_tab_bytes + sizeof(u64) * alloc > TAB_BUDGET_BYTES) {
+            // over budget: drop every table (cudaFree waits for the kernels that still read them).  Plans hold
+            // table pointers, so they go too; the caller of get_plan rebuilds what it needs.
+            for (auto &kv : g_tab) cudaFree(kv.second.ptr);
+            g_tab.clear();
+            g_tab_bytes = 0;
+            g_tab_generation.fetch_add(1);
+        }
         B2S_CUDA(cudaMalloc(&e.ptr, sizeof(u64) * alloc));
+        g_tab_bytes += sizeof(u64) * alloc;
         table4_kernel<<<(alloc + 255) / 256, 256, 0, st>>>(e.ptr, t.base, alloc, key.kind, key.log_l);
         B2S_LAUNCHED();
         // once per table: block until it is built, so that later calls on ANY stream can use it
@@ -174,6 +187,7 @@ struct PlanKey {
 struct CachedPlan {
     Pass4Plan plan[3];
     int npass;
+    u64 generation;  // of the table cache its pointers come from
 };
 std::mutex g_plan_mu;
 std::map<PlanKey, CachedPlan> g_plans;
@@ -187,24 +201,32 @@ int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale,
     const PlanKey key{w, do_scale ? scale : 1, n_in, log_n, (inverse ? 1u : 0u) | (do_scale ? 2u : 0u) | (log_E << 2), dev};
     std::lock_guard<std::mutex> lk(g_plan_mu);
     auto it = g_plans.find(key);
+    if (it != g_plans.end() && it->second.generation != g_tab_generation.load()) {
+        g_plans.erase(it);  // its tables were dropped (table-cache budget)
+        it = g_plans.end();
+    }
     if (it == g_plans.end()) {
         if (g_plans.size() > 4096) g_plans.clear();  // bounded: callers with ever-changing roots
         CachedPlan cp;
         cp.npass = plan4(log_n, n_in, w, scale, inverse, do_scale, 2, log_E, cp.plan);
         int rc = 0;
-        for (int ps = 0; ps < cp.npass; ++ps) {
-            Pass4Plan &pl = cp.plan[ps];
-            auto bind = [&](const Tab4 &t, const u64 *&dst) {
-                if (t.used && rc == 0) rc = get_table(t, st, &dst);
-            };
-            bind(pl.tw_tail, pl.P.tw_tail);
-            bind(pl.tw_core[0], pl.P.tw_core[0]);
-            bind(pl.tw_core[1], pl.P.tw_core[1]);
-            bind(pl.in_scale, pl.P.in_scale);
-            bind(pl.out_scale, pl.P.out_scale);
-            bind(pl.tw_lo, pl.P.tw_lo);
-            bind(pl.tw_hi, pl.P.tw_hi);
-            bind(pl.col_scale, pl.P.col_scale);
+        for (int attempt = 0; attempt < 2; ++attempt) {  // a table that overflows the budget drops the earlier ones
+            cp.generation = g_tab_generation.load();
+            for (int ps = 0; ps < cp.npass; ++ps) {
+                Pass4Plan &pl = cp.plan[ps];
+                auto bind = [&](const Tab4 &t, const u64 *&dst) {
+                    if (t.used && rc == 0) rc = get_table(t, st, &dst);
+                };
+                bind(pl.tw_tail, pl.P.tw_tail);
+                bind(pl.tw_core[0], pl.P.tw_core[0]);
+                bind(pl.tw_core[1], pl.P.tw_core[1]);
+                bind(pl.in_scale, pl.P.in_scale);
+                bind(pl.out_scale, pl.P.out_scale);
+                bind(pl.tw_lo, pl.P.tw_lo);
+                bind(pl.tw_hi, pl.P.tw_hi);
+                bind(pl.col_scale, pl.P.col_scale);
+            }
+            if (rc || cp.generation == g_tab_generation.load()) break;
         }
         if (rc) return rc;
         it = g_plans.emplace(key, cp).first;
@@ -272,6 +294,8 @@ void ntt_cache_clear() {
         cudaFree(kv.second.ptr);
     }
     g_tab.clear();
+    g_tab_bytes = 0;
+    g_tab_generation.fetch_add(1);
 }
 
 int ntt_run(const u64 *d_in, u64 in_stride, u32 n_in, u64 *d_out, u64 out_stride, u32 log_n, u32 n_planes, u64 omega,

@@ -76,6 +76,13 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
     global _state
     if _state is not None:
         return _state["glue"]
+    import pickle
+    if pickle.DEFAULT_PROTOCOL != 4:
+        # The reference hashes pickle.dumps(leaf) with the interpreter's default protocol; the device-side leaf
+        # emitter (csrc/leaf.cuh) and the templates of marshal.py reproduce protocol 4's framing and integer
+        # opcodes (CPython 3.8 - 3.13).  Under another default the reference's own bytes change as well.
+        raise RuntimeError("stark_brainfuck_b200 reproduces pickle protocol 4 (CPython 3.8-3.13); this interpreter's "
+                           "default protocol is %d" % pickle.DEFAULT_PROTOCOL)
     if reference_dir is not None and reference_dir not in sys.path:
         sys.path.insert(0, reference_dir)
     mods = {name: importlib.import_module(name)

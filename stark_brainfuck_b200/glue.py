@@ -552,7 +552,7 @@ class Glue:
         return (np.asarray(mono_off, dtype=np.uint32), np.asarray(coeffs, dtype=np.uint64).reshape(-1, 3), factors)
 
     def _table_planes(self, codewords, width, N):
-        """(width, 3, N) device tensor of a table's codewords.  Columns that came out of a device op inside
+        """((width, 3, N) device tensor of a table's codewords, flags of the lifted base-field columns among them).  Columns that came out of a device op inside
         keep_planes() are copied on the device, the others marshalled; inside keep_planes() the assembled tensor
         is kept for the table's next call (boundary, transition and terminal quotients read the same lists)."""
         eng = self.engine
@@ -562,8 +562,9 @@ class Glue:
             ent = self._kept.get(key)
             if ent is not None and ent[0] is codewords and len(ent[2]) == width and \
                     all(a is b for a, b in zip(ent[2], codewords)):
-                return ent[1]
+                return ent[1], ent[3]
         cw = eng.alloc((width, 3, N))
+        base_columns = np.zeros(width, dtype=np.uint8)  # columns known to be lifted base-field codewords
         for j in range(width):
             planes = self.planes_of(codewords[j])
             lifted = self.lifted_planes_of(codewords[j]) if planes is None else None
@@ -572,11 +573,12 @@ class Glue:
             elif lifted is not None:  # a base-field codeword lifted element by element: c0 = the plane, c1 = c2 = 0
                 eng.copy(cw[j, 0:1], lifted)
                 eng.zero(cw[j, 1:3])
+                base_columns[j] = 1
             else:
                 eng.upload_into(cw[j], self.B.xfe_to_np(codewords[j]))
         if key is not None:
-            self._kept[key] = (codewords, cw, list(codewords[:width]))
-        return cw
+            self._kept[key] = (codewords, cw, list(codewords[:width]), base_columns)
+        return cw, base_columns
 
     def quotient_codewords(self, domain, codewords, width, constraints, kind, height=0, omicron_inv=1, shift=0):
         """code/table.py:155-178 / :190-236 / :253-286: [mpo.evaluate(point_i) * lift(zerofier_inverse[i])]
@@ -585,9 +587,9 @@ class Glue:
         n_vars = 2 * width if kind == ZEROFIER_TRANSITION else width
         program = self.compile_constraints(constraints, n_vars)
         xfield = codewords[0][0].field  # acc = point[0].field.zero() (code/multivariate.py:106)
-        cw = self._table_planes(codewords, width, N)
+        cw, base_columns = self._table_planes(codewords, width, N)
         out, vanishes = self.engine.quotients(cw, shift, *program, kind, height, omicron_inv, domain.offset.value,
-                                              domain.omega.value)
+                                              domain.omega.value, base_columns=base_columns)
         # code/ntt.py:178-179
         assert not vanishes, "batch inverse does not work when input contains a zero"
         if self._kept is not None:

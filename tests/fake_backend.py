@@ -182,9 +182,12 @@ class FakeLib:
 
 
     def b2s_quotients(self, d_cw, N, width, shift, nc, h_off, h_coeffs, h_factors, max_factors, kind, height, oinv,
-                      offset, omega, d_out, h_flag, stream):
+                      offset, omega, d_out, h_flag, h_base_columns, stream):
         self.launches += 1
         cw = _u64(_addr(d_cw), width * 3 * N).reshape(width, 3, N)
+        if _addr(h_base_columns):  # the caller's claim must hold, or the device would silently drop planes 1 and 2
+            flags = _u8(_addr(h_base_columns), width)
+            assert not cw[flags != 0, 1:, :].any(), "a column flagged base-field has non-zero upper planes"
         off = np.ctypeslib.as_array((C.c_uint32 * (nc + 1)).from_address(_addr(h_off)))
         m = int(off[nc])
         coeffs = _u64(_addr(h_coeffs), 3 * m).reshape(m, 3) if m else np.zeros((0, 3), dtype=np.uint64)

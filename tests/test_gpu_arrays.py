@@ -289,13 +289,20 @@ def test_quotients_golden_and_oracle(eng):
             program.append(cons)
         from util import quotient_program
         prog = quotient_program(program)
-        d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
-        for kind, height in ((2, 8), (2, 0)):
-            oinv = pow(root_of_unity(3), P - 2, P)
-            out, vanishes = eng.quotients(d, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
-            ref, rv = orc.quotients(cw, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
-            assert vanishes == rv is False
-            assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref)
+        for lifted in (False, True):
+            if lifted:  # every other column is a lifted base-field column; some monomials get base-field coefficients
+                cw[::2, 1:, :] = 0
+                for cons in program:
+                    for mono in cons[::2]:
+                        mono[1][1] = mono[1][2] = 0
+                prog = quotient_program(program)
+            d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
+            for kind, height in ((2, 8), (2, 0)):
+                oinv = pow(root_of_unity(3), P - 2, P)
+                out, vanishes = eng.quotients(d, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
+                ref, rv = orc.quotients(cw, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
+                assert vanishes == rv is False
+                assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (logn, lifted, kind, height)
     # offset 1 puts x = 1 on the domain: boundary zerofier vanishes
     name, cw, shift, prog, kind, height, oinv, want = next(iter(quotient_cases(g)))
     W, _, N = cw.shape
@@ -402,16 +409,26 @@ def test_quotients_with_the_brainfuck_air_programs(eng):
     w = root_of_unity(logn)
     for ti, t in enumerate(air["tables"]):
         W = t["full_width"]
-        cw = np.stack([rand_xfe(3000 + 17 * ti + j, N) for j in range(W)])
-        d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
-        for kind, name in ((1, "boundary"), (2, "transition"), (3, "terminal")):
-            prog = quotient_program(t[name])
-            height = 64
-            oinv = pow(root_of_unity(6), P - 2, P)
-            out, vanishes = eng.quotients(d, N // height, *prog, kind, height, oinv, 7, w)
-            ref, rv = orc.quotients(cw, N // height, *prog, kind, height, oinv, 7, w)
-            assert not vanishes and not rv
-            assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (t["name"], name)
+        for lifted in (False, True):
+            cw = np.stack([rand_xfe(3000 + 17 * ti + j, N) for j in range(W)])
+            if lifted:
+                # what BrainfuckStark.prove() hands over: base columns lifted into the extension field (zero upper
+                # planes) -- the kernel's base-field fast path; one extension column with a few base-field values
+                cw[:t["base_width"], 1:, :] = 0
+                cw[W - 1, 1:, ::7] = 0
+            d = eng.upload(cw.reshape(3 * W, N)).reshape(W, 3, N)
+            for kind, name in ((1, "boundary"), (2, "transition"), (3, "terminal")):
+                prog = quotient_program(t[name])
+                height = 64
+                oinv = pow(root_of_unity(6), P - 2, P)
+                out, vanishes = eng.quotients(d, N // height, *prog, kind, height, oinv, 7, w)
+                ref, rv = orc.quotients(cw, N // height, *prog, kind, height, oinv, 7, w)
+                assert not vanishes and not rv
+                assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (t["name"], name, lifted)
+                if lifted:  # the caller's own flags instead of the library's scan (what the glue passes)
+                    flags = [j < t["base_width"] for j in range(W)]
+                    out, _ = eng.quotients(d, N // height, *prog, kind, height, oinv, 7, w, base_columns=flags)
+                    assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (t["name"], name, "flags")
 
 
 def test_open_multi_matches_single_calls(eng):

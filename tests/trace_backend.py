@@ -122,7 +122,7 @@ SPECS = {
                    lambda a: []),
     "b2s_quotients": (["d", "s", "s", "s", "s", ("hi", lambda a: 4 * (a[4] + 1)), ("hi", lambda a: 24 * _q_monos(a)),
                        ("hi", lambda a: 4 * _q_monos(a) * a[8]), "s", "s", "s", "s", "s", "s", "d", ("ho", lambda a: 4),
-                       "S"], lambda a: [(14, 0, 3 * a[4], 8 * a[1], 8 * a[1])]),
+                       ("hi", lambda a: a[2]), "S"], lambda a: [(14, 0, 3 * a[4], 8 * a[1], 8 * a[1])]),
     "b2s_open_multi": (["hp7", ("hi", lambda a: 8 * a[7]), "s", "hp7", ("hi", lambda a: 8 * a[7]),
                         ("hi", lambda a: 4 * a[7]), ("hi", lambda a: 8 * int(_open_counts(a).sum())), "s",
                         ("ho", lambda a: 8 * int(_open_counts(a).sum()) * a[2]), ("ho", _open_path_bytes), "S"],
@@ -234,7 +234,8 @@ class TracingLib:
                     enc.append({"ptrs": [rec.locate(int(p)) for p in ptrs]})
                 elif k[0] == "hi":
                     nb = k[1](scal)
-                    enc.append({"h": rec.blob(C.string_at(_address(x), nb)) if nb and _address(x) else None})
+                    enc.append({"h": rec.blob(C.string_at(_address(x), nb)) if nb and _address(x) else None,
+                                "null": _address(x) == 0})
                 elif k[0] == "ho":
                     enc.append({"o": k[1](scal)})
             rc = fn(*args)
@@ -380,6 +381,9 @@ def replay(path, engine, urandom_seed=1234, check_kernels=True, check_reads=True
                     keep.append(arr)
                     args.append(arr.ctypes.data_as(C.c_void_p))
                 elif k[0] == "hi":
+                    if e["h"] is None and e.get("null"):
+                        args.append(None)
+                        continue
                     buf = C.create_string_buffer(data_of(e["h"]) + b"\0" * 8)
                     keep.append(buf)
                     args.append(C.cast(buf, C.c_void_p))
