@@ -44,3 +44,28 @@ int merkle_field_run(const u64 *d_planes, u64 stride, u64 n, const b2s_leaf_temp
                      cudaStream_t st);
 int merkle_upper_run(u8 *d_nodes, u64 npo2, cudaStream_t st);
 int merkle_upload_templates(const b2s_leaf_templates *tpl, cudaStream_t st);
+
+// ---- programmatic dependent launch (chains of small dependent kernels: tree levels, FRI rounds) ---------------
+// A kernel launched with launch_pdl() may start while its predecessor in the stream is still running; it must
+// execute pdl_wait() before it touches anything an earlier kernel wrote.  What precedes the wait (index arithmetic,
+// staging constant tables) overlaps the predecessor's tail, and the launch latency disappears behind it.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif

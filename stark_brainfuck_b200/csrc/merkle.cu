@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(LEAF_THREADS)
     u8 *msgs = smem_raw + ((sizeof(LeafTplSmem) + 15) & ~(size_t)15);
     leaf_tpl_to_smem(tpl, lm, tp);
     __syncthreads();
+    pdl_wait();  // the codeword (the previous round's fold) may still be in flight
+    pdl_trigger();
     const u64 base = (u64)blockIdx.x * LEAF_THREADS;
     const u64 i = base + threadIdx.x;
     if (nodes && i < 4) reinterpret_cast<ulonglong2 *>(nodes)[i] = make_ulonglong2(0, 0);  // slot 0 is never a node
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(LEAF_THREADS)
 // nodes[first .. first+count) from their children: one thread per node (large levels)
 __global__ void __launch_bounds__(128) merkle_level_kernel(u8 *nodes, u64 first, u64 count) {
     const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     if (j >= count) return;
     u64 h[8];
     node_digest(nodes, first + j, h);
@@ -108,6 +112,8 @@ __global__ void __launch_bounds__(REDUCE_NODES / 2) merkle_reduce_kernel(u8 *nod
     const u32 cnt = count < REDUCE_NODES ? (u32)count : REDUCE_NODES;
     const u64 heap0 = count + (u64)blockIdx.x * cnt;
     const u32 half = cnt >> 1;
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x < half) {
         u64 h[8];
         node_digest(nodes, (heap0 >> 1) + threadIdx.x, h);
@@ -315,8 +321,8 @@ int launch_leaf2(const u64 *d_planes, u64 stride, u64 n, const PreparedLeaf *pl,
         attr[dev & 15] = true;
     }
     const unsigned blocks = (unsigned)((n + LEAF_THREADS - 1) / LEAF_THREADS);
-    leaf_subtree_kernel<NSLOTS, MB, FOLD, SUBTREE><<<blocks, LEAF_THREADS, smem, st>>>(d_planes, stride, n, pl->tpl,
-                                                                                       pl->lm, F, d_nodes);
+    B2S_CUDA(launch_pdl(leaf_subtree_kernel<NSLOTS, MB, FOLD, SUBTREE>, dim3(blocks), dim3(LEAF_THREADS), smem, st, d_planes,
+                        stride, n, pl->tpl, pl->lm, F, d_nodes));
     B2S_LAUNCHED();
     return 0;
 }
@@ -340,12 +346,12 @@ int merkle_upper_run(u8 *d_nodes, u64 npo2, cudaStream_t st) {
     u64 cnt = npo2;
     while (cnt > LEVEL_MIN_NODES) {  // large levels: full parallelism, one launch each
         cnt >>= 1;
-        merkle_level_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(d_nodes, cnt, cnt);
+        B2S_CUDA(launch_pdl(merkle_level_kernel, dim3((unsigned)((cnt + 127) / 128)), dim3(128), 0, st, d_nodes, cnt, cnt));
         B2S_LAUNCHED();
     }
     while (cnt > 1) {  // the top: 8 levels per launch
         const u64 per = cnt < REDUCE_NODES ? cnt : REDUCE_NODES;
-        merkle_reduce_kernel<<<(unsigned)(cnt / per), REDUCE_NODES / 2, 0, st>>>(d_nodes, cnt);
+        B2S_CUDA(launch_pdl(merkle_reduce_kernel, dim3((unsigned)(cnt / per)), dim3(REDUCE_NODES / 2), 0, st, d_nodes, cnt));
         B2S_LAUNCHED();
         cnt /= per;
     }

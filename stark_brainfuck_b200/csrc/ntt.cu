@@ -17,6 +17,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.h"
 #include "ntt4_plan.h"
@@ -25,8 +26,10 @@ namespace {
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
-template <int TL, int LE>
-__global__ void __launch_bounds__(LE == 4 ? 512 : 1024, LE == 4 ? 2 : 1)
+// WIDE = true: the same pass compiled for at most 256 threads per CTA and up to 128 registers per thread.  A lone
+// vector puts only ~14 warps on an SM, so registers are free and the scheduler may keep more butterflies in flight.
+template <int TL, int LE, bool WIDE>
+__global__ void __launch_bounds__(WIDE ? 256 : (LE == 4 ? 512 : 1024), WIDE ? 2 : (LE == 4 ? 2 : 1))
     ntt4_pass_kernel(const __grid_constant__ Pass4Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 R = 1u << P.log_R;
@@ -236,8 +239,8 @@ int get_plan(u32 log_n, u64 n_in, u64 w, u64 scale, bool inverse, bool do_scale,
     return 0;
 }
 
-template <int TL, int LE>
-int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
+template <int TL, int LE, bool WIDE>
+int launch_pass4w(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     const Pass4Params &P = pl.P;
     const size_t smem = sizeof(u64) * ((TL > 0 ? ((size_t)1 << P.log_R) : 0) + pass4_core_table_elems(LE, P.a, 0) +
                                        pass4_core_table_elems(LE, P.a, 1) + pass4_smem_elems(P.log_R, P.log_T, LE)) + 16;
@@ -245,7 +248,8 @@ int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr_done[dev & 15] < smem) {
-        B2S_CUDA(cudaFuncSetAttribute(ntt4_pass_kernel<TL, LE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2S_CUDA(cudaFuncSetAttribute(ntt4_pass_kernel<TL, LE, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
         attr_done[dev & 15] = smem;
     }
     cudaLaunchConfig_t cfg = {};
@@ -257,10 +261,24 @@ int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pl.first ? 0 : 1;  // the first pass depends on whatever the caller enqueued before
-    B2S_CUDA(cudaLaunchKernelEx(&cfg, ntt4_pass_kernel<TL, LE>, P));
+    // Every pass, the first one included, is a programmatic dependent launch: what precedes griddepcontrol.wait in
+    // the kernel (barrier set-up, TMA of the constant twiddle tables) touches nothing an earlier kernel of the stream
+    // produces, and the wait itself returns only when that kernel has completed and flushed.
+    static const char *pdl_first = getenv("B2S_NTT_PDL_FIRST");
+    cfg.numAttrs = (pl.first && pdl_first && pdl_first[0] == '0') ? 0 : 1;
+    B2S_CUDA(cudaLaunchKernelEx(&cfg, ntt4_pass_kernel<TL, LE, WIDE>, P));
     B2S_LAUNCHED();
     return 0;
+}
+
+template <int TL, int LE>
+int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
+    static const char *force = getenv("B2S_NTT_WIDE");
+    const u32 threads = pass4_threads(pl.P.log_R, pl.P.log_T, LE);
+    const u64 ctas = (u64)pl.grid_x * pl.grid_y * n_planes;
+    const bool wide = force ? force[0] == '1' : (threads <= 256 && ctas <= 2 * 148);
+    if (wide && threads <= 256) return launch_pass4w<TL, LE, true>(pl, n_planes, st);
+    return launch_pass4w<TL, LE, false>(pl, n_planes, st);
 }
 
 int dispatch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
@@ -282,9 +300,44 @@ int dispatch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     return B2S_ERR_ARG;
 }
 
+// The intermediate vector of a multi-pass transform.  One buffer per (device, stream), kept between calls: calls on a
+// stream are ordered, so they can share it, and without an allocation / release pair between two transforms the
+// first pass of the next one is launched right behind the last pass of this one (programmatic dependent launch).
+struct WorkBuf {
+    u64 *ptr = nullptr;
+    size_t bytes = 0;
+};
+std::mutex g_work_mu;
+std::map<std::pair<int, cudaStream_t>, WorkBuf> g_work;
+
+int get_work(size_t bytes, cudaStream_t st, u64 **out) {
+    int dev = 0;
+    B2S_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_work_mu);
+    if (g_work.size() > 64) {  // many short-lived streams: do not accumulate their buffers
+        for (auto &kv : g_work) cudaFreeAsync(kv.second.ptr, kv.first.second);
+        g_work.clear();
+    }
+    WorkBuf &w = g_work[{dev, st}];
+    if (w.bytes < bytes) {
+        if (w.ptr) cudaFreeAsync(w.ptr, st);
+        w.ptr = nullptr;
+        w.bytes = 0;
+        B2S_CUDA(cudaMallocAsync(&w.ptr, bytes, st));
+        w.bytes = bytes;
+    }
+    *out = w.ptr;
+    return 0;
+}
+
 }  // namespace
 
 void ntt_cache_clear() {
+    {
+        std::lock_guard<std::mutex> lk(g_work_mu);
+        for (auto &kv : g_work) cudaFree(kv.second.ptr);
+        g_work.clear();
+    }
     {
         std::lock_guard<std::mutex> lk(g_plan_mu);
         g_plans.clear();
@@ -358,7 +411,10 @@ int ntt_run(const u64 *d_in, u64 in_stride, u32 n_in, u64 *d_out, u64 out_stride
     int rc = get_plan(log_n, n_in, w, scale, inverse != 0, do_scale, log_E, st, plan, &npass);
     if (rc) return rc;
     u64 *work = nullptr;
-    if (npass > 1) B2S_CUDA(cudaMallocAsync(&work, sizeof(u64) * n * n_planes, st));
+    if (npass > 1) {
+        rc = get_work(sizeof(u64) * n * n_planes, st, &work);
+        if (rc) return rc;
+    }
     for (int ps = 0; ps < npass && rc == 0; ++ps) {
         Pass4Plan &pl = plan[ps];
         pl.P.in = pl.first ? d_in : work;
@@ -367,6 +423,5 @@ int ntt_run(const u64 *d_in, u64 in_stride, u32 n_in, u64 *d_out, u64 out_stride
         pl.P.out_plane_stride = pl.last ? out_stride : n;
         rc = dispatch_pass4(pl, n_planes, st);
     }
-    if (work) cudaFreeAsync(work, st);
     return rc;
 }

@@ -10,7 +10,7 @@ time lives in every importing module's globals.  install() therefore
      fast_multiply & co. pick them up) and in every loaded module whose global IS the original;
   3. patches class attributes, which every importer shares: Polynomial.scale/evaluate_domain,
      Fri.Domain.evaluate/xevaluate/interpolate/xinterpolate, Fri.commit/query/query_last/prove,
-     Merkle.__init__/open  (Merkle.root/verify and Fri.verify stay the reference's).
+     Merkle.__init__/open, ExtensionField.lift  (Merkle.root/verify and Fri.verify stay the reference's).
   4. next rows: Table.*_quotients / PermutationArgument.quotient, SaltedMerkle.__init__, and the
      nonlinear combination.  The combination is INLINE in BrainfuckStark.prove
      (code/brainfuck_stark.py:241-298), so there is no attribute to rebind: prove() is recompiled
@@ -126,6 +126,22 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
     set_attr(Fri, "prove", lambda self, codeword, proof_stream: glue.fri_prove(self, codeword, proof_stream))
     set_attr(Merkle, "__init__", lambda self, data_array: glue.merkle_build(self, data_array))
     set_attr(Merkle, "open", lambda self, index: glue.merkle_open(self, index))
+
+    # ExtensionField.lift (code/extension_field.py:113-116).  Every Table.extend lifts its base
+    # codewords element by element (e.g. code/io_table.py:106-107): 2.1 M calls in a Hello-World proof, each through
+    # three constructors and two Polynomial.degree() scans.  Same object graph, built directly: the element wraps
+    # the base element ITSELF as its only coefficient, or no coefficient when it is zero (code/extension_field.py:6-9).
+    X, Pn = binding.ExtensionFieldElement, binding.Polynomial
+
+    def lift(self, base_field_element):
+        if type(base_field_element) == X:
+            return base_field_element
+        p = Pn.__new__(Pn)
+        p.__dict__ = {"coefficients": [base_field_element] if base_field_element.value != 0 else []}
+        x = X.__new__(X)
+        x.__dict__ = {"polynomial": p, "field": self}
+        return x
+    set_attr(binding.ExtensionField, "lift", lift)
 
     # -- 4. next row: quotient codewords of the AIR ---------------------------
     # DEBUG keeps the reference's own loops (they print and assert degree bounds on the way).
