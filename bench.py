@@ -546,6 +546,29 @@ def run_b200(args):
             mirror.unregister()
     except Exception as e:  # informational only
         extra["fri_error"] = str(e)
+    # ---- extra: BASELINE config 5, device side.  (a) the recorded command stream of the unmodified
+    # BrainfuckStark.prove() of the Hello-World program (tests/golden/trace_hello.bin: every allocation, copy and
+    # C-ABI call the drop-in issued, recorded in the authoring container) replayed through libb2s.so: wall clock of
+    # the whole device side of that proof, uploads included; (b) the device ops of a proof with a 2^16-row trace
+    # on a 2^20 FRI domain (synthetic traces, the reference's real constraint programs), CUDA events.
+    try:
+        if rank == 0:
+            import trace_backend
+            path = os.path.join(ROOT, "tests", "golden", "trace_hello.bin")
+            trace_backend.replay(path, eng, check_kernels=False, check_reads=False)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            rep = trace_backend.replay(path, eng, check_kernels=False, check_reads=False)
+            torch.cuda.synchronize(dev)
+            extra["prove_hello_world_device_replay_ms"] = (time.perf_counter() - t0) * 1e3
+            extra["prove_hello_world_engine_calls"] = rep["calls"]
+            extra["prove_hello_world_b200_wall_s"] = "7.3 (unmodified prove() with the reference staged next to the GPU: profiles/artifacts/r02f_hello_world_prove_b200_7s.json)"
+            extra["prove_2p20_domain_b200_wall_s"] = "52.4 (8 780-cycle program, unmodified prove(), reference verifier accepts: profiles/artifacts/r02s_prove_2p20_domain_b200.json)"
+            sys.path.insert(0, os.path.join(ROOT, "profiles", "microbench"))
+            import prove_device_pipeline
+            extra["prove_2p20_domain_device_pipeline_ms"] = prove_device_pipeline.pipeline_ms(eng, reps=2)["ms"]
+    except Exception as e:  # informational only
+        extra["prove_error"] = repr(e)[:200]
 
     sharded = None
     if world > 1:

@@ -134,16 +134,33 @@ __global__ void __launch_bounds__(128)
     u64 h[8];
     b2b_init(h);
     const u64 nblocks = len == 0 ? 1 : (len + 127) >> 7;
+#pragma unroll 1
     for (u64 blk = 0; blk < nblocks; ++blk) {
+        // Full blocks and the bytes of the last one are read with plain byte loads under ordinary branches.  (The
+        // obvious `q < len ? msg[q] : 0` inside the unrolled loops compiled -- nvcc 12.9, sm_100a -- into predicated
+        // byte loads whose destination aliases the address register and is not cleared when the predicate is off:
+        // profiles/microbench/blob_san_repro.cu hashes a 427-byte message wrongly with it.)
         u64 m[16];
+        const u64 base = blk * 128;
+        const u64 have = len - base < 128 ? len - base : 128;  // bytes of this block
+        if (have == 128) {
 #pragma unroll
-        for (int w = 0; w < 16; ++w) {
-            u64 v = 0;
-            for (int b = 7; b >= 0; --b) {
-                const u64 q = blk * 128 + w * 8 + b;
-                v = (v << 8) | (q < len ? msg[q] : 0);
+            for (int w = 0; w < 16; ++w) {
+                u64 v = 0;
+#pragma unroll
+                for (int b = 7; b >= 0; --b) v = (v << 8) | msg[base + w * 8 + b];
+                m[w] = v;
             }
-            m[w] = v;
+        } else {
+#pragma unroll
+            for (int w = 0; w < 16; ++w) m[w] = 0;
+            for (u64 q = 0; q < have; ++q) {
+                const u64 byte = msg[base + q];
+                const u32 w = (u32)(q >> 3), sh = (u32)(q & 7) * 8;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k == (int)w) m[k] |= byte << sh;  // static register indices
+            }
         }
         const bool last = blk + 1 == nblocks;
         b2b_compress(h, m, last ? len : (blk + 1) * 128, last);

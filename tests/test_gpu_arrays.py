@@ -563,3 +563,20 @@ def test_row_leaves_vs_oracle(eng):
     orc.row_leaves(one, modes2[:6], tpl, seg_off, 1, w1)
     n1, _ = eng.merkle_rows([eng.upload(a)[0] for a in one], modes2[:6], tpl, seg_off, 1)
     assert eng.download_bytes(n1)[64:] == w1[1:].tobytes()
+
+
+def test_blob_leaf_digests_every_length(eng):
+    """b2s_merkle_blobs leaf digests for every preimage length 0..600 against hashlib (one leaf per tree and many per
+    tree).  Round 2 found a miscompiled conditional byte load in this kernel (profiles/microbench/blob_san_repro.cu)
+    that only showed under compute-sanitizer: the tail of the last block is now read under ordinary branches."""
+    R = random.Random(11)
+    blobs = [bytes(R.getrandbits(8) for _ in range(L)) for L in range(0, 601)]
+    n = len(blobs)
+    npo2 = 1024
+    nodes = np.frombuffer(eng.download_bytes(eng.merkle_blobs(blobs)), dtype=np.uint8).reshape(-1, 64)
+    for i, b in enumerate(blobs):
+        assert bytes(nodes[npo2 + i]) == hashlib.blake2b(b).digest(), len(b)
+    for L in (0, 1, 127, 128, 129, 385, 427, 512, 513):
+        one = np.frombuffer(eng.download_bytes(eng.merkle_blobs([blobs[L]])), dtype=np.uint8).reshape(-1, 64)
+        assert bytes(one[1]) == hashlib.blake2b(blobs[L]).digest(), L
+    assert n == 601
