@@ -49,8 +49,9 @@ def shard_coset_evaluate(engine, coeffs, log_n, omega, offset, rank, world, grou
     code/ntt.py:164-168): rank r computes the residue class r of the output,
         out[G t + r] = sum_j (c_j (offset omega^r)^j) (omega^G)^(j t),      t < n / G,
     a size-n/G coset transform of the coefficients with offset offset*omega^r and root omega^G -- no exchange.
-    When the polynomial has more than n/G coefficients they are scaled by (offset omega^r)^j and folded modulo
-    n/G first.  coeffs: (1, m) base-field or (3, m) extension-field planes on the device, replicated on every
+    With up to 2 n/G coefficients the rank transforms on the twice finer coset and keeps the even outputs; with
+    more they are scaled by (offset omega^r)^j and folded modulo n/G first (one polynomial per call then).
+    coeffs: (q, m) planes on the device (a base-field polynomial per plane; an extension-field one is three), replicated on every
     rank -- or, with gather_coefficients=True, this rank's contiguous 1/G of them (one all-gather of the small
     coefficient vector is then the only collective).  Returns (q, n/G) planes: element t is output G t + r."""
     G = world
@@ -61,13 +62,20 @@ def shard_coset_evaluate(engine, coeffs, log_n, omega, offset, rank, world, grou
         dist.all_gather_into_tensor(full, coeffs.contiguous().view(-1), group=group)
         coeffs = full.view(G, q, m_loc).permute(1, 0, 2).reshape(q, G * m_loc).contiguous()
     q, m = coeffs.shape
-    assert q in (1, 3)
     log_g = G.bit_length() - 1
     n_loc = 1 << (log_n - log_g)
     w_g = pow(omega, G, P)
     off_r = offset * pow(omega, rank, P) % P
     if m <= n_loc:
-        return engine.ntt(coeffs, log_n - log_g, w_g, offset=off_r)
+        return engine.ntt(coeffs, log_n - log_g, w_g, offset=off_r)  # any number of planes: one batched call
+    if m <= 2 * n_loc:
+        # Twice as many coefficients as local points (expansion factor G/2): the transform of length 2 n/G on the
+        # coset offset*omega^r with root omega^(G/2) has the wanted values at its even outputs.  It computes twice
+        # the outputs the rank keeps, but takes every plane of a trace in ONE call, where scaling and folding
+        # each polynomial separately (below) is latency-bound (46 planes on 8 GPUs: 2.7 ms against 0.9 on one).
+        full = engine.ntt(coeffs, log_n - log_g + 1, pow(omega, G // 2, P), offset=off_r)
+        return full[:, ::2].contiguous()
+    assert q in (1, 3)
     # more coefficients than local points: x^(n/G) = (offset omega^r)^(n/G) on this residue class after scaling,
     # i.e. scale first, then add the chunks of n/G coefficients on top of each other (b2s_combination with unit
     # weights does the modular sum), then a plain transform
