@@ -478,5 +478,13 @@ def case_salted(env, glue=None):
             assert [t.nodes[npo2 + i] for i in range(len(data))] == want
             salt, path = t.open(1)
             assert sm.SaltedMerkle.verify(t.root(), 1, salt, path, data[1])
+        if glue is not None:
+            # leaves that are a codeword living on the device (this used to hit an unbound local)
+            from stark_brainfuck_b200.glue import DeviceCodeword
+            xs = rand_xfe_list(env, 9, 8)
+            dc = DeviceCodeword(glue, glue.engine.upload(glue.B.xfe_to_np(xs)), env.xfield)
+            t = sm.SaltedMerkle(dc)
+            want = [hashlib.blake2b(pickle.dumps(e) + pickle.dumps(s_)).digest() for e, s_ in t.leafs]
+            assert [t.nodes[8 + i] for i in range(8)] == want and triples([e for e, _ in t.leafs]) == triples(xs)
     finally:
         sm.urandom = old
