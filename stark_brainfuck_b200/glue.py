@@ -1090,19 +1090,24 @@ class NodeView:
         """the leaf indices whose authentication path is not completely cached yet"""
         if depth == 0:
             return []
-        need = [i for i in dict.fromkeys(indices)
-                if any((((1 << depth) | i) >> j) ^ 1 not in self._cache for j in range(depth))]
-        return [i for i in need if 0 <= i < (1 << depth)]
+        cache, top = self._cache, 1 << depth
+        need = [i for i in dict.fromkeys(indices) if 0 <= i < top]
+        if len(cache) > 1:  # (a fresh tree holds at most its root: everything is wanted)
+            need = [i for i in need if any(((top | i) >> j) ^ 1 not in cache for j in range(depth))]
+        return need
 
     def fill_paths(self, need, paths, depth):
-        """paths[q][j]: the 64-byte sibling at level j of leaf need[q] (bytes, or rows of a uint8 array)"""
-        for i, path in zip(need, paths):
+        """paths[q][j]: the 64-byte sibling at level j of leaf need[q] (lists of bytes, or a (len, depth, 64) uint8
+        array)"""
+        cache, limit = self._cache, self._npo2 + self._n
+        raw = paths.tobytes() if hasattr(paths, "tobytes") else None  # one conversion, then slices
+        for q, i in enumerate(need):
             k = (1 << depth) | i
+            at = q * depth * 64
             for j in range(depth):
                 sib = (k >> j) ^ 1
-                if sib not in self._cache and not (sib >= self._npo2 + self._n):
-                    v = path[j]
-                    self._cache[sib] = v if isinstance(v, bytes) else v.tobytes()
+                if sib not in cache and sib < limit:
+                    cache[sib] = raw[at + 64 * j:at + 64 * j + 64] if raw is not None else bytes(paths[q][j])
 
     def prefetch_paths(self, indices, depth):
         need = self.wanted_paths(indices, depth)
