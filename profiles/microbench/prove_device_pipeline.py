@@ -34,6 +34,16 @@ def pipeline_ms(eng, log_h=16, log_n=20, reps=3):
                 for t in tables]
     progs = [[quotient_program(t[k]) for k in ("boundary", "transition", "terminal")] for t in tables]
     rnd = eng.upload(rng.integers(0, P, (3, N // 4), dtype=np.uint64))
+    from stark_brainfuck_b200 import marshal
+    m = mirror
+    fields = [m.algebra.BaseField.main() for _ in tables]
+    row_b = tuple([m.binding.make_xfe(5, 6, 7, m.xfield)] +
+                  [m.algebra.BaseFieldElement(3 + j, f) for t, f in zip(tables, fields) for j in range(t["base_width"])])
+    row_x = tuple(m.binding.make_xfe(5 + j, 6, 7, m.xfield)
+                  for j in range(sum(t["full_width"] - t["base_width"] for t in tables)))
+    tplb, tplx = marshal.row_template(m.binding, row_b), marshal.row_template(m.binding, row_x)
+    frame = marshal.salt_frame(bytes(range(24)))
+    salts = eng.upload_bytes(rng.integers(0, 256, (N, 24), dtype=np.uint8))
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def run():
@@ -51,9 +61,13 @@ def pipeline_ms(eng, log_h=16, log_n=20, reps=3):
             base_cw.append(eng.ntt(eng.ntt(tb, log_h, omicron, inverse=True), log_n, w, offset=7))
             ext_cw.append(eng.ntt(eng.ntt(tx, log_h, omicron, inverse=True), log_n, w, offset=7))
         mark("lde+ldex (46 columns)")
-        eng.merkle_field(rcw, tpl)
-        eng.merkle_field(ext_cw[0][:3], tpl)
-        mark("2 trees (stand-ins for the salted ones)")
+        # the two salted trees over zipped rows (code/brainfuck_stark.py:178-180, :197-199): randomizer + 16 base
+        # columns, then the 10 extension columns; row templates derived from the mirror's classes as the glue does
+        base_planes = [rcw[0], rcw[1], rcw[2]] + [b[i] for b in base_cw for i in range(b.shape[0])]
+        eng.merkle_rows(base_planes, tplb.modes, tplb.tpl, tplb.seg_off, N, salts, frame[0], frame[1])
+        ext_planes = [x[i] for x in ext_cw for i in range(x.shape[0])]
+        eng.merkle_rows(ext_planes, tplx.modes, tplx.tpl, tplx.seg_off, N, salts, frame[0], frame[1])
+        mark("2 salted row trees (17- and 10-tuples)")
         quotients, assembled = [], []
         for t, bc, xc in zip(tables, base_cw, ext_cw):
             W = t["full_width"]

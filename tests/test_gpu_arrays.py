@@ -557,6 +557,21 @@ def test_row_leaves_vs_oracle(eng):
     want = orc.merkle_upper(want)
     got = np.frombuffer(eng.download_bytes(nodes), dtype=np.uint8).reshape(2 * n, 64)
     assert np.array_equal(got[1:], want[1:])
+    # rows whose preimages differ in length by far more than the kernel's ring allows a thread to run ahead of its
+    # warp (40 integers of 2 bytes against 40 of 11): the byte-by-byte path at the end of the kernel
+    n2 = 512
+    wide = [np.array([(R.randrange(256) if (i // 3) % 2 else R.randrange(1 << 63, P)) for i in range(n2)], dtype=np.uint64)
+            for _ in range(40)]
+    segs3 = [bytes(R.getrandbits(8) for _ in range(R.randrange(0, 40))) for _ in range(41)]
+    tpl3, seg3 = b"".join(segs3), np.cumsum([0] + [len(x) for x in segs3]).astype(np.uint32)
+    modes3 = np.zeros(40, dtype=np.uint8)
+    want3 = np.zeros((2 * n2, 64), dtype=np.uint8)
+    assert len(orc.row_leaves(wide, modes3, tpl3, seg3, n2, want3, salts[:n2], pre, suf)) == 0
+    want3 = orc.merkle_upper(want3)
+    nodes3, exc3 = eng.merkle_rows([eng.upload(a)[0] for a in wide], modes3, tpl3, seg3, n2, eng.upload_bytes(salts[:n2]),
+                                   pre, suf)
+    assert len(exc3) == 0
+    assert eng.download_bytes(nodes3)[64:] == want3[1:].tobytes()
     # unsalted rows, one leaf
     one = [a[:1].copy() for a in planes[:6]]
     w1 = np.zeros((2, 64), dtype=np.uint8)
