@@ -121,7 +121,14 @@ extern "C" int b2s_combination(const uint64_t *const *h_cols, const uint64_t *h_
                           (unsigned long long)h_strides[c]);
             return B2S_ERR_ARG;
         }
-    const int K = N >= 1024 ? 4 : 1;
+    // points per thread: 2 (64 registers, three CTAs per SM) beats 4 (96 registers) at every size measured on a
+    // B200 -- 2^16: 0.25 vs 0.32 ms, 2^18: 0.46 vs 0.60, 2^20: 1.19 vs 1.21 for the AIR's 76 columns -- and 1
+    static const char *force_k = getenv("B2S_COMB_K");
+    const int K = N < 1024 ? 1 : (force_k ? atoi(force_k) : 2);
+    if (K != 1 && K != 2 && K != 4) {
+        b2s_set_error("combination: B2S_COMB_K must be 1, 2 or 4");
+        return B2S_ERR_ARG;
+    }
     const u64 T = N / K;
     // group the columns by shift; columns without a shifted term form slot 0
     std::vector<u32> order(n_cols);
@@ -179,6 +186,8 @@ extern "C" int b2s_combination(const uint64_t *const *h_cols, const uint64_t *h_
     const unsigned grid = (unsigned)((T + 255) / 256);
     if (K == 4)
         comb_kernel<4><<<grid, 256, 0, st>>>(d_slots, (u32)slots.size(), d_cols, T, d_out, out_stride);
+    else if (K == 2)
+        comb_kernel<2><<<grid, 256, 0, st>>>(d_slots, (u32)slots.size(), d_cols, T, d_out, out_stride);
     else
         comb_kernel<1><<<grid, 256, 0, st>>>(d_slots, (u32)slots.size(), d_cols, T, d_out, out_stride);
     B2S_LAUNCHED();
