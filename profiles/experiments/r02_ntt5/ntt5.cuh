@@ -18,8 +18,9 @@
 // place in shared memory (a thread overwrites exactly what it read).  The column is stored as 16 rows of
 // B + Q elements: the Q pad elements make the 64-bit accesses of all three steps conflict-free per half warp.
 // Global traffic is done in TILE ORDER (lanes along the Tc adjacent columns: 8 Tc contiguous bytes per row)
-// through shared memory: pass 1 loads with cp.async, both passes store their tile the same way; pass 2 reads
-// its contiguous rows straight into registers.
+// through shared memory by all 8 B threads of the CTA (n5_tile_thread: four instructions per element): pass 1 loads
+// with cp.async, both passes store their tile the same way; pass 2 reads its contiguous rows straight into
+// registers.
 // The inter-pass twiddle w^(c k) is a product of two table entries (W^i, i < 1024, and W^(1024 i)); the
 // second table carries n^-1 for the inverse transform, which therefore costs nothing extra.
 // Phase functions are __host__ __device__: tests/ntt5_hostcheck.cpp runs them thread by thread on the CPU.
@@ -139,11 +140,12 @@ GL_HD void n5_step3_compute_store(u64 (&v)[16], u64 *Sc, const u32 t, const Pass
     }
 }
 
-// ---- tile-order global <-> shared: element idx = row * 8 + col slot ----------------------------------------------
-// (the kernel issues these with cp.async / plain stores; the host check copies)
+// ---- tile-order global <-> shared ----------------------------------------------------------------------------
+// The CTA has 8 B threads.  Thread tid moves column slot tid & 7 of the rows (tid >> 3) + B i, i < 16: a warp touches
+// 4 adjacent rows x 8 adjacent columns (8 Tc contiguous bytes per row), and because (tid >> 3) < B the shared-memory
+// position of row (tid >> 3) + B i is i * ROW + (tid >> 3) -- both addresses advance by a constant per step.
 template <int LOG_R>
-GL_HD bool n5_tile_elem(const u32 idx, const u32 ncols, u32 &row, u32 &col) {
-    col = idx & (N5_SLOTS - 1);
-    row = idx >> 3;
-    return col < ncols && row < (u32)N5<LOG_R>::R;
+GL_HD void n5_tile_thread(const u32 tid, u32 &slot, u32 &row0) {
+    slot = tid & (N5_SLOTS - 1);
+    row0 = tid >> 3;
 }

@@ -32,7 +32,7 @@ template <int LOG_R>
 static void emulate_pass(const Pass5Plan &pl, u32 n_planes) {
     using N = N5<LOG_R>;
     const Pass5Params &P = pl.P;
-    std::vector<u64> S((size_t)P.Tc * N::CS);
+    std::vector<u64> S((size_t)N5_SLOTS * N::CS);
     std::vector<u64> regs((size_t)P.Tc * N::B * 16);
     for (u32 plane = 0; plane < n_planes; ++plane)
         for (u32 bx = 0; bx < pl.grid_x; ++bx) {
@@ -42,10 +42,12 @@ static void emulate_pass(const Pass5Plan &pl, u32 n_planes) {
             const u64 *in = P.in + (u64)plane * P.in_plane_stride;
             u64 *out = P.out + (u64)plane * P.out_plane_stride;
             if (!P.last)
-                for (u32 idx = 0; idx < (u32)N::R * N5_SLOTS; ++idx) {
-                    u32 row, c;
-                    if (n5_tile_elem<LOG_R>(idx, ncols, row, c))
-                        S[c * N::CS + n5_pos<LOG_R>(row)] = in[((u64)row << P.log_C) + c0 + c];
+                for (u32 tid = 0; tid < (u32)N::B * N5_SLOTS; ++tid) {
+                    u32 slot, row0;
+                    n5_tile_thread<LOG_R>(tid, slot, row0);
+                    if (slot >= ncols) continue;
+                    for (u32 i = 0; i < 16; ++i)
+                        S[slot * N::CS + i * N::ROW + row0] = in[((u64)(row0 + N::B * i) << P.log_C) + c0 + slot];
                 }
             for (u32 col = 0; col < ncols; ++col)
                 for (u32 t = 0; t < (u32)N::B; ++t) {
@@ -74,10 +76,12 @@ static void emulate_pass(const Pass5Plan &pl, u32 n_planes) {
                     memcpy(v, &regs[((size_t)col * N::B + t) * 16], sizeof(v));
                     n5_step3_compute_store<LOG_R>(v, S.data() + col * N::CS, t, P, c0 + col);
                 }
-            for (u32 idx = 0; idx < (u32)N::R * N5_SLOTS; ++idx) {
-                u32 row, c;
-                if (n5_tile_elem<LOG_R>(idx, ncols, row, c))
-                    out[((u64)row << P.log_C) + c0 + c] = S[c * N::CS + n5_pos<LOG_R>(row)];
+            for (u32 tid = 0; tid < (u32)N::B * N5_SLOTS; ++tid) {
+                u32 slot, row0;
+                n5_tile_thread<LOG_R>(tid, slot, row0);
+                if (slot >= ncols) continue;
+                for (u32 i = 0; i < 16; ++i)
+                    out[((u64)(row0 + N::B * i) << P.log_C) + c0 + slot] = S[slot * N::CS + i * N::ROW + row0];
             }
         }
 }

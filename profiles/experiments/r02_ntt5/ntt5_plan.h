@@ -13,7 +13,7 @@ struct Pass5Plan {
 
 // plain transforms (no coset scale, no zero padding) of 2^16 .. 2^22 points
 static inline bool plan5_supported(u32 log_n, u64 n_in, bool do_scale) {
-    return log_n >= 16 && log_n <= 22 && n_in == ((u64)1 << log_n) && !do_scale;
+    return log_n >= 16 && log_n <= 22 && n_in == ((u64)1 << log_n) && !do_scale;  // (8 B = 1024 threads at R = 2^11)
 }
 
 // w: the root actually used (omega, or omega^-1 for the inverse).  n_sm: SMs to spread a single vector over.
@@ -37,11 +37,10 @@ static inline void plan5(u32 log_n, u64 w, bool inverse, u32 n_planes, u32 n_sm,
         u32 tc = n_planes == 1 ? (P.C + n_sm - 1) / n_sm : N5_SLOTS;
         if (tc < 1) tc = 1;
         if (tc > N5_SLOTS) tc = N5_SLOTS;
-        if (tc * B > 1024) tc = 1024 / B;
         P.Tc = tc;
         pl.grid_x = (P.C + tc - 1) / tc;
-        pl.threads = tc * B < 32 ? 32 : tc * B;
-        pl.smem = sizeof(u64) * ((size_t)tc * (16 * (B + (B >> 4)) + 2) + ((size_t)1 << log_R) + B) + 16;
+        pl.threads = N5_SLOTS * B;  // all eight slots' threads move the tile; slots >= Tc idle while it is transformed
+        pl.smem = sizeof(u64) * ((size_t)N5_SLOTS * (16 * (B + (B >> 4)) + 2) + ((size_t)1 << log_R) + B) + 16;
         const u64 wR = gl_pow(w, n >> log_R);  // primitive R-th root of this pass
         pl.tw1.used = pl.tw1.two_d = true;
         pl.tw1.base = wR;
