@@ -54,8 +54,9 @@ def main(name):
     dropin.uninstall()
     assert bfs.verify(proof), "the reference verifier rejects the recorded proof"
     sha = hashlib.sha256(proof).hexdigest()
-    if name == "pppp":
-        assert sha == json.load(open(os.path.join(HERE, "bfs.json")))["proof_sha256"]
+    all_reference = {"pppp": "bfs.json", "io": "bfs_io.json"}  # proofs of the all-Python reference (make_golden.py)
+    if name in all_reference:
+        assert sha == json.load(open(os.path.join(HERE, all_reference[name])))["proof_sha256"]
     if name in EXPECTED:
         assert sha == EXPECTED[name], sha
     meta = {"program": source, "inputs": inputs, "urandom_seed": 1234, "running_time": running_time,

@@ -18,7 +18,7 @@ from util import GOLDEN  # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name,domain,min_calls", [("pppp", 1024, 70), ("hello", 1 << 17, 80)])
+@pytest.mark.parametrize("name,domain,min_calls", [("pppp", 1024, 70), ("io", 2048, 70), ("hello", 1 << 17, 80)])
 def test_prove_command_stream_replays_bit_exact(name, domain, min_calls):
     from stark_brainfuck_b200 import Engine
     path = os.path.join(GOLDEN, "trace_%s.bin" % name)

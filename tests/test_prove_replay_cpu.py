@@ -10,7 +10,7 @@ import trace_backend as tb
 from util import GOLDEN
 
 
-@pytest.mark.parametrize("name", ["pppp"])
+@pytest.mark.parametrize("name", ["pppp", "io"])
 def test_replay_reproduces_every_recorded_output(name):
     from fake_backend import fake_engine
     path = os.path.join(GOLDEN, "trace_%s.bin" % name)
