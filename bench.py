@@ -565,7 +565,7 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
             extra["prove_hello_world_device_replay_ms"] = (time.perf_counter() - t0) * 1e3
             extra["prove_hello_world_engine_calls"] = rep["calls"]
-            extra["prove_hello_world_b200_wall_s"] = "7.3 (unmodified prove() with the reference staged next to the GPU: profiles/artifacts/r02f_hello_world_prove_b200_7s.json)"
+            extra["prove_hello_world_b200_wall_s"] = "6.7 (unmodified prove() with the reference staged next to the GPU: profiles/artifacts/r02al_hello_world_prove_b200_6.7s.json)"
             extra["prove_2p20_domain_b200_wall_s"] = "52.4 (8 780-cycle program, unmodified prove(), reference verifier accepts: profiles/artifacts/r02s_prove_2p20_domain_b200.json)"
             sys.path.insert(0, os.path.join(ROOT, "profiles", "microbench"))
             import prove_device_pipeline
