@@ -472,6 +472,18 @@ def run_b200(args):
         extra["batched_32_planes_hbm_gbs"] = 16.0 * n * q / (ms_b / 1e3) / 1e9
     except Exception as e:  # informational only
         extra["batched_error"] = str(e)
+    # ---- extra: BASELINE config 3, the cubic extension-field transform of 2^18 points (three planes, one call)
+    try:
+        lg3 = 18
+        x3 = torch.randint(0, 2 ** 62, (3, 1 << lg3), dtype=torch.int64, device=dev)
+        y3 = eng.empty(3, 1 << lg3)
+        w3 = root_of_unity(lg3)
+        eng.ntt(x3, lg3, w3, out=y3)
+        ms3, _ = eng.ntt_timed(x3, lg3, w3, out=y3, iters=20)
+        extra["xfe_ntt_2p18_fwd_ms"] = ms3
+        extra["xfe_ntt_2p18_hbm_gbs"] = 48.0 * (1 << lg3) / (ms3 / 1e3) / 1e9
+    except Exception as e:  # informational only
+        extra["xfe_ntt_error"] = str(e)
     # ---- extra: independent round trips issued round-robin on four streams (what a caller with many single
     # vectors and no batch to hand over gets: the kernels of different transforms fill each other's idle SMs)
     try:

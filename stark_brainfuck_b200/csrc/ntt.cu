@@ -276,7 +276,7 @@ int launch_pass4(const Pass4Plan &pl, u32 n_planes, cudaStream_t st) {
     static const char *force = getenv("B2S_NTT_WIDE");
     const u32 threads = pass4_threads(pl.P.log_R, pl.P.log_T, LE);
     const u64 ctas = (u64)pl.grid_x * pl.grid_y * n_planes;
-    const bool wide = force ? force[0] == '1' : (threads <= 256 && ctas <= 2 * 148);
+    const bool wide = force ? force[0] == '1' : (threads <= 256 && ctas <= 3 * 148);  // (3 x 2^18: 21.6 vs 22.6 us)
     if (wide && threads <= 256) return launch_pass4w<TL, LE, true>(pl, n_planes, st);
     return launch_pass4w<TL, LE, false>(pl, n_planes, st);
 }
