@@ -8,6 +8,8 @@
 // one thread evaluates one (constraint, point) pair in extension-field arithmetic; the inverse
 // zerofier is computed once per point by a first kernel.  HBM-bound only in name: a point reads
 // 24 B per variable it uses and writes 24 B, the monomial arithmetic dominates.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -277,15 +279,6 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
                 return B2S_ERR_ARG;
             }
         }
-    // the program: a few KB, uploaded per call
-    u32 *d_off = nullptr, *d_fac = nullptr, *d_hot = nullptr;
-    u64 *d_coef = nullptr, *d_zinv = nullptr;
-    int *d_flag = nullptr;
-    B2S_CUDA(cudaMallocAsync(&d_off, sizeof(u32) * (n_constraints + 1), st));
-    B2S_CUDA(cudaMallocAsync(&d_coef, sizeof(u64) * (3 * (size_t)n_mono + 1), st));
-    B2S_CUDA(cudaMallocAsync(&d_zinv, sizeof(u64) * N, st));
-    B2S_CUDA(cudaMallocAsync(&d_flag, sizeof(int), st));
-    B2S_CUDA(cudaMemcpyAsync(d_off, h_mono_off, sizeof(u32) * (n_constraints + 1), cudaMemcpyHostToDevice, st));
     // which codewords are lifted base-field columns: the caller's word for it (it zeroed the upper planes itself),
     // else an exact scan of the columns
     std::vector<u32> kinds(width, 0);
@@ -369,15 +362,25 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
     }
     prog_off[n_constraints] = (u32)code.size();
     code.push_back(0);
-    u32 *d_poff = nullptr;
-    B2S_CUDA(cudaMallocAsync(&d_fac, sizeof(u32) * code.size(), st));
-    B2S_CUDA(cudaMallocAsync(&d_poff, sizeof(u32) * (n_constraints + 1), st));
-    B2S_CUDA(cudaMemcpyAsync(d_fac, code.data(), sizeof(u32) * code.size(), cudaMemcpyHostToDevice, st));
-    B2S_CUDA(cudaMemcpyAsync(d_poff, prog_off.data(), sizeof(u32) * (n_constraints + 1), cudaMemcpyHostToDevice, st));
-    if (n_mono) B2S_CUDA(cudaMemcpyAsync(d_coef, scaled.data(), sizeof(u64) * 3 * (size_t)n_mono, cudaMemcpyHostToDevice, st));
-    B2S_CUDA(cudaMallocAsync(&d_hot, sizeof(u32) * n_constraints, st));
-    B2S_CUDA(cudaMemcpyAsync(d_hot, hot.data(), sizeof(u32) * n_constraints, cudaMemcpyHostToDevice, st));
-    B2S_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    // The program, a few KB: ONE allocation and ONE upload per call (five separate ones cost more host time than the
+    // small tables' kernels take):  coefficients | zero flag, pad | mono_off | prog_off | hot | code
+    const size_t n_coef = 3 * (size_t)n_mono + 1;
+    std::vector<u64> blob(n_coef + 1 + ((size_t)2 * (n_constraints + 1) + n_constraints + code.size() + 1) / 2 + 1, 0);
+    memcpy(blob.data(), scaled.data(), sizeof(u64) * 3 * (size_t)n_mono);
+    u32 *words = reinterpret_cast<u32 *>(blob.data() + n_coef + 1);
+    memcpy(words, h_mono_off, sizeof(u32) * (n_constraints + 1));
+    memcpy(words + (n_constraints + 1), prog_off.data(), sizeof(u32) * (n_constraints + 1));
+    memcpy(words + 2 * (n_constraints + 1), hot.data(), sizeof(u32) * n_constraints);
+    memcpy(words + 2 * (n_constraints + 1) + n_constraints, code.data(), sizeof(u32) * code.size());
+    u64 *d_blob = nullptr, *d_zinv = nullptr;
+    B2S_CUDA(cudaMallocAsync(&d_blob, sizeof(u64) * blob.size(), st));
+    B2S_CUDA(cudaMallocAsync(&d_zinv, sizeof(u64) * N, st));
+    B2S_CUDA(cudaMemcpyAsync(d_blob, blob.data(), sizeof(u64) * blob.size(), cudaMemcpyHostToDevice, st));
+    const u64 *d_coef = d_blob;
+    int *d_flag = reinterpret_cast<int *>(d_blob + n_coef);
+    const u32 *d_words = reinterpret_cast<const u32 *>(d_blob + n_coef + 1);
+    const u32 *d_off = d_words, *d_poff = d_words + (n_constraints + 1), *d_hot = d_words + 2 * (n_constraints + 1);
+    const u32 *d_fac = d_hot + n_constraints;
     ZeroParams Z;
     u64 sq = omega;
     for (int b = 0; b < 32; ++b) {
@@ -404,13 +407,8 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
     B2S_LAUNCHED();
     int flag = 0;
     B2S_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    cudaFreeAsync(d_off, st);
-    cudaFreeAsync(d_fac, st);
-    cudaFreeAsync(d_poff, st);
-    cudaFreeAsync(d_hot, st);
-    cudaFreeAsync(d_coef, st);
+    cudaFreeAsync(d_blob, st);
     cudaFreeAsync(d_zinv, st);
-    cudaFreeAsync(d_flag, st);
     B2S_CUDA(cudaStreamSynchronize(st));
     if (h_zero_flag) *h_zero_flag = flag;
     return 0;
