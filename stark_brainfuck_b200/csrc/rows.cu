@@ -67,8 +67,8 @@ __device__ __forceinline__ u64 read8(const u8 *p) {
 // compressed when EVERY thread of the warp has completed it, so the compression never runs with a partial warp
 // (the first version compressed whenever a thread's own block filled up: positions differ by the integers' lengths,
 // the warps diverged at every block boundary, 18 ms for the two trees of a 2^20-domain proof).  A thread may run
-// ahead of the slowest one by ROW_RB * 128 - 136 bytes; rows that differ more (only contrived ones do: nine bytes per
-// integer at most) leave the fast path and are redone byte by byte at the end.
+// ahead of the slowest one by ROW_RB * 128 - 160 = 96 bytes; rows that differ more (only contrived ones do: nine bytes
+// per integer at most) leave the fast path and are redone byte by byte at the end.
 __global__ void __launch_bounds__(ROW_THREADS) row_leaf_kernel(const __grid_constant__ RowParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *ring = reinterpret_cast<u64 *>(smem_raw) + threadIdx.x;  // word i of this thread at ring[i * ROW_THREADS]
@@ -139,8 +139,25 @@ __global__ void __launch_bounds__(ROW_THREADS) row_leaf_kernel(const __grid_cons
         append(w, n);
         flush();
     };
-    auto put_segment = [&](u32 a, u32 b) {  // template bytes [a, b): the same for every thread
-        for (; a + 8 <= b; a += 8) put(read8(tpl + a), 8);
+    // template bytes [a, b): the same for every thread.  Whole words keep a thread's byte offset within the open word,
+    // so the two shifts are set up once per segment; the warp votes every fourth word (32 bytes of the ring's slack).
+    auto put_segment = [&](u32 a, u32 b) {
+        const u32 sh = 8 * (pos & 7);
+        u32 c = 0;
+        for (; a + 8 <= b; a += 8, ++c) {
+            const u64 w = read8(tpl + a);
+            if (live && !ovf) {
+                if (pos + 8 > (done + ROW_RB) * 128) {
+                    ovf = true;
+                } else {
+                    ring[((pos >> 3) & (ROW_RW - 1)) * ROW_THREADS] = acc | (w << sh);
+                    acc = (w >> 1) >> (63 - sh);  // w >> (64 - sh), and 0 when sh == 0
+                    pos += 8;
+                }
+            }
+            if ((c & 3) == 3) flush();
+        }
+        flush();
         if (a < b) put(read8(tpl + a) & (~0ull >> (64 - 8 * (b - a))), b - a);
     };
     auto put_int = [&](u64 v) {  // CPython save_long, protocol 4 (see leaf.cuh): one or two words, chosen per thread
