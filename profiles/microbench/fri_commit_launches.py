@@ -32,3 +32,20 @@ for _ in range(4):
     t = e0.elapsed_time(e2)
     best = t if best is None else min(best, t)
 print("FRI commit 2^20, device side: %.3f ms" % best)
+# per round, warm, back to back (CUDA events between the rounds)
+ev = [torch.cuda.Event(enable_timing=True)]
+ev[0].record()
+eng.merkle_field(cw0, tpl)
+ev.append(torch.cuda.Event(enable_timing=True))
+ev[-1].record()
+cw, N, w, off = cw0, n, root_of_unity(logn), 7
+sizes = [n]
+while N // 2 > 4:
+    cw, _nodes = eng.fri_fold(cw, [3, 5, 7], off, w, tpl)
+    N //= 2
+    w, off = w * w % P, off * off % P
+    ev.append(torch.cuda.Event(enable_timing=True))
+    ev[-1].record()
+    sizes.append(N)
+torch.cuda.synchronize()
+print("per round (leaves: us):", ", ".join("%d: %.1f" % (sz, 1e3 * ev[i].elapsed_time(ev[i + 1])) for i, sz in enumerate(sizes)))
