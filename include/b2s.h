@@ -190,10 +190,14 @@ int b2s_gather(const uint64_t *d_planes, uint64_t plane_stride, uint32_t n_plane
  * factors h_factors[m * max_factors + f] = (variable << 8) | exponent, exponent 0 = unused.
  * d_out: n_constraints codewords in the same plane layout.  *h_zero_flag is set to 1 when a
  * zerofier vanishes on the domain (the reference's batch_inverse asserts, code/ntt.py:178-179).
+ * h_zero_flag may be NULL when the caller has ruled that out itself (offset^N != 1 puts every point
+ * outside the subgroup the zerofiers' roots live in): the call then reads nothing back and does not
+ * synchronise, so consecutive tables' kernels run back to back.
  * h_base_columns (HOST, `width` bytes, or NULL): non-zero for a codeword the caller KNOWS to be a lifted
  * base-field column, i.e. with all-zero planes 1 and 2 (every Table.extend of the reference lifts its base
  * codewords, e.g. code/io_table.py:106-107); their factors are multiplied in the base field (1 multiplication
- * instead of 9).  NULL: the library scans the columns itself.  Synchronises. */
+ * instead of 9).  NULL: the library scans the columns itself (one read-back).  Synchronises unless
+ * h_zero_flag is NULL and h_base_columns is given. */
 #define B2S_ZEROFIER_BOUNDARY 1
 #define B2S_ZEROFIER_TRANSITION 2
 #define B2S_ZEROFIER_TERMINAL 3

@@ -79,7 +79,8 @@ def pipeline_ms(eng, log_h=16, log_n=20, reps=3):
         for t, cw, pr in zip(tables, assembled, progs):
             flags = [j < t["base_width"] for j in range(t["full_width"])]  # what Glue._table_planes knows
             for kind in (1, 2, 3):
-                out, _ = eng.quotients(cw, N // h, *pr[kind - 1], kind, h, oinv, 7, w, base_columns=flags)
+                out, _ = eng.quotients(cw, N // h, *pr[kind - 1], kind, h, oinv, 7, w, base_columns=flags,
+                                       check_zerofier=False)  # offset^N != 1: decided on the host, as the glue does
                 quotients.append(out)
         mark("quotients (47 constraints, 5 tables, 15 calls)")
         cols = [rcw] + [b[i:i + 1] for b in base_cw for i in range(b.shape[0])]

@@ -405,11 +405,16 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
     quotient_kernel<<<dim3((unsigned)((N + Q_THREADS - 1) / Q_THREADS), n_constraints), Q_THREADS, 0, st>>>(
         d_cw, N, width, shift, d_off, d_coef, d_fac, d_poff, d_hot, d_zinv, d_out);
     B2S_LAUNCHED();
+    if (!h_zero_flag) {  // the caller has ruled a vanishing zerofier out: nothing to read back, the call stays asynchronous
+        cudaFreeAsync(d_blob, st);
+        cudaFreeAsync(d_zinv, st);
+        return 0;
+    }
     int flag = 0;
     B2S_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     cudaFreeAsync(d_blob, st);
     cudaFreeAsync(d_zinv, st);
     B2S_CUDA(cudaStreamSynchronize(st));
-    if (h_zero_flag) *h_zero_flag = flag;
+    *h_zero_flag = flag;
     return 0;
 }

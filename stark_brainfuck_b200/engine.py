@@ -275,11 +275,13 @@ class Engine:
 
     # ---- quotient codewords ---------------------------------
     def quotients(self, cw, shift, mono_off, coeffs, factors, kind, height, omicron_inv, offset, omega,
-                  base_columns=None):
+                  base_columns=None, check_zerofier=True):
         """code/table.py:155-286 for one table.  cw: (width, 3, N) int64 device tensor; the constraint
         program as numpy arrays (mono_off (C+1,) uint32, coeffs (M, 3) uint64, factors (M, F) uint32).
         base_columns: optional per-codeword flags, True where the caller knows planes 1 and 2 are zero (a lifted
         base-field column); None lets the library scan.
+        check_zerofier=False: the caller has ruled out a zerofier vanishing on the domain; the flag is not read
+        back and the call does not synchronise.
         Returns ((C, 3, N) device tensor, True if a zerofier vanishes on the domain)."""
         width, three, N = cw.shape
         assert three == 3 and cw.is_contiguous()
@@ -293,7 +295,7 @@ class Engine:
         self.check(self.lib.b2s_quotients(_ptr(cw), N, width, shift, nc, mono_off.ctypes.data_as(C.c_void_p),
                                           coeffs.ctypes.data_as(C.c_void_p), factors.ctypes.data_as(C.c_void_p),
                                           factors.shape[1] if factors.size else 0, kind, height, omicron_inv, offset,
-                                          omega, _ptr(out), C.byref(flag),
+                                          omega, _ptr(out), C.byref(flag) if check_zerofier else None,
                                           None if base is None else base.ctypes.data_as(C.c_void_p), self.stream_ptr()))
         return out, bool(flag.value)
 

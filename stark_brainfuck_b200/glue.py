@@ -580,6 +580,21 @@ class Glue:
             self._kept[key] = (codewords, cw, list(codewords[:width]), base_columns)
         return cw, base_columns
 
+    @staticmethod
+    def _zerofier_may_vanish(domain, kind, height, omicron_inv):
+        """False when no zerofier of code/table.py:161-163, :194-201, :256-259 can vanish on offset * <omega>, decided
+        on the host: the roots (1, the powers of omicron, omicron^-1) are N-th roots of unity when omicron^N = 1,
+        and no point of the domain is one when offset^N != 1.  The engine then skips its read-back of the
+        device's own check (code/ntt.py:178-179) and the tables' kernels run back to back."""
+        N = domain.length
+        if N < 1 or pow(int(domain.omega.value), N, P) != 1 or pow(int(domain.offset.value), N, P) == 1:
+            return True
+        if kind == ZEROFIER_BOUNDARY:
+            return False
+        if kind == ZEROFIER_TRANSITION:  # x^height = 1 implies x^N = 1 when height divides N
+            return height <= 0 or N % height != 0
+        return pow(int(omicron_inv), N, P) != 1
+
     def quotient_codewords(self, domain, codewords, width, constraints, kind, height=0, omicron_inv=1, shift=0):
         """code/table.py:155-178 / :190-236 / :253-286: [mpo.evaluate(point_i) * lift(zerofier_inverse[i])]
         for every constraint over the whole FRI domain, on the device."""
@@ -589,7 +604,9 @@ class Glue:
         xfield = codewords[0][0].field  # acc = point[0].field.zero() (code/multivariate.py:106)
         cw, base_columns = self._table_planes(codewords, width, N)
         out, vanishes = self.engine.quotients(cw, shift, *program, kind, height, omicron_inv, domain.offset.value,
-                                              domain.omega.value, base_columns=base_columns)
+                                              domain.omega.value, base_columns=base_columns,
+                                              check_zerofier=self._zerofier_may_vanish(domain, kind, height,
+                                                                                       omicron_inv))
         # code/ntt.py:178-179
         assert not vanishes, "batch inverse does not work when input contains a zero"
         if self._kept is not None:

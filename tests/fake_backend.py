@@ -196,7 +196,10 @@ class FakeLib:
         out, flag = orc.quotients(cw, shift, off, coeffs, fac, kind, height, oinv, offset, omega)
         if nc:
             _u64(_addr(d_out), nc * 3 * N).reshape(nc, 3, N)[:] = out
-        _set_i32(h_flag, flag)
+        if _addr(h_flag):
+            _set_i32(h_flag, flag)
+        else:  # the caller claimed no zerofier can vanish on this domain and skipped the read-back: hold it to that
+            assert not flag, "b2s_quotients called without a zero flag, but a zerofier vanishes on the domain"
         return 0
 
     def b2s_open_multi(self, h_planes, h_strides, n_planes, h_nodes, h_npo2, h_counts, h_indices, n_sets, h_values,

@@ -428,6 +428,38 @@ def case_quotients_glue(env, glue):
             scope.__exit__(None, None, None)
 
 
+def case_zerofier_decision(env, glue):
+    """Glue._zerofier_may_vanish (the host-side replacement of the device flag's read-back) against brute force over
+    small domains: whenever it answers False, no zerofier of code/table.py:161-163, :194-201, :256-259 has a root on
+    offset * <omega>; and the reference's own configuration (offset = the field's generator) takes the fast path."""
+    from stark_brainfuck_b200.glue import ZEROFIER_BOUNDARY, ZEROFIER_TERMINAL, ZEROFIER_TRANSITION
+    P = env.field.p
+    gen = env.field.generator().value
+    skipped = 0
+    for log_n in (2, 3, 5):
+        N = 1 << log_n
+        w = env.field.primitive_nth_root(N).value
+        roots = [pow(w, i, P) for i in range(N)]
+        for offset in (gen, 1, w, pow(w, 3, P), pow(gen, N, P), pow(env.field.primitive_nth_root(2 * N).value, 1, P), 7):
+            dom = env.Fri.Domain(env.field(offset), env.field(w), N)
+            pts = [offset * r % P for r in roots]
+            for height in (0, 1, 2, N // 2, N, 3, 2 * N):
+                omicron = env.field.primitive_nth_root(height).value if height in (1, 2, N // 2, N, 2 * N) and height else 1
+                for oinv in (pow(omicron, P - 2, P), offset, 5):
+                    truth = {ZEROFIER_BOUNDARY: any(x == 1 for x in pts),
+                             ZEROFIER_TRANSITION: height == 0 or any(pow(x, height, P) == 1 for x in pts),
+                             ZEROFIER_TERMINAL: any(x == oinv for x in pts)}
+                    for kind, vanishes in truth.items():
+                        may = glue._zerofier_may_vanish(dom, kind, height, oinv)
+                        assert may or not vanishes, (N, offset, kind, height, oinv)
+                        skipped += not may
+    assert skipped > 100
+    big = env.Fri.Domain(env.field(gen), env.field.primitive_nth_root(1 << 20), 1 << 20)
+    oinv = env.field.primitive_nth_root(1 << 16).inverse().value
+    assert not any(glue._zerofier_may_vanish(big, k, 1 << 16, oinv)
+                   for k in (ZEROFIER_BOUNDARY, ZEROFIER_TRANSITION, ZEROFIER_TERMINAL))
+
+
 def salted_rows(env, case):
     """the rows of a tests/golden/salted.json case, rebuilt with one BaseField object per field_id"""
     fields, cols = {}, []

@@ -74,5 +74,9 @@ def test_quotients_through_the_glue(env, mirror_cpu):
     fc.case_quotients_glue(env, mirror_cpu.glue())
 
 
+def test_zerofier_decision_on_the_host(env, mirror_cpu):
+    fc.case_zerofier_decision(env, mirror_cpu.glue())
+
+
 def test_salted_row_trees(env, mirror_cpu):
     fc.case_salted(env, mirror_cpu.glue())

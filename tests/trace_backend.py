@@ -236,12 +236,12 @@ class TracingLib:
                     nb = k[1](scal)
                     enc.append({"h": rec.blob(C.string_at(_address(x), nb)) if nb and _address(x) else None,
                                 "null": _address(x) == 0})
-                elif k[0] == "ho":
-                    enc.append({"o": k[1](scal)})
+                elif k[0] == "ho":  # a NULL output pointer (b2s_quotients' optional flag) is recorded as such
+                    enc.append({"o": k[1](scal), "null": True} if _address(x) == 0 else {"o": k[1](scal)})
             rc = fn(*args)
             outs = []
             for i, k in enumerate(kinds):
-                if not isinstance(k, str) and k[0] == "ho":
+                if not isinstance(k, str) and k[0] == "ho" and _address(a[i]):
                     outs.append({"arg": i, "sha": _sha(C.string_at(_address(a[i]), k[1](scal)))})
             devs = []
             if rc == 0:
@@ -388,6 +388,9 @@ def replay(path, engine, urandom_seed=1234, check_kernels=True, check_reads=True
                     keep.append(buf)
                     args.append(C.cast(buf, C.c_void_p))
                 elif k[0] == "ho":
+                    if e.get("null"):
+                        args.append(None)
+                        continue
                     buf = C.create_string_buffer(e["o"] + 8)
                     outs[i] = (buf, e["o"])
                     sig = _lib.SIGNATURES[name][1][i]
