@@ -4,10 +4,10 @@
 // code/permutation_argument.py:11-20: every constraint is a multivariate polynomial
 // (code/multivariate.py: dict exponent-vector -> coefficient) that the reference evaluates at
 // every point of the FRI domain with MPolynomial.evaluate (code/multivariate.py:105-116) and
-// divides by a zerofier.  Here the host flattens the dictionaries into a monomial program and
-// one thread evaluates one (constraint, point) pair in extension-field arithmetic; the inverse
+// divides by a zerofier.  Here the host re-factors every dictionary into a Horner program
+// (quotient_prog.h) that one thread runs for one constraint at two points; the inverse
 // zerofier is computed once per point by a first kernel.  HBM-bound only in name: a point reads
-// 24 B per variable it uses and writes 24 B, the monomial arithmetic dominates.
+// 8 or 24 B per variable it uses and writes 24 B, the field arithmetic dominates.
 #include <stdlib.h>
 #include <string.h>
 
@@ -94,54 +94,68 @@ __global__ void __launch_bounds__(256) column_kind_kernel(const u64 *__restrict_
     if (__syncthreads_or(any != 0) && threadIdx.x == 0) kinds[v] = 0;
 }
 
-// One thread evaluates one (constraint, point) pair and multiplies by the inverse zerofier.
+// One thread evaluates one constraint at K points and multiplies by the inverse zerofier.
 //
 // The reference hands every constraint over EXPANDED, a dictionary exponent vector -> coefficient
 // (code/multivariate.py), and evaluates it monomial by monomial (:105-116).  The AIR's polynomials are products of
 // a few shared forms (instruction selectors x instruction-specific relations, code/processor_table.py:130-217),
-// so the host re-factors them: a greedy multivariate Horner scheme
+// so the host re-factors them (quotient_prog.h): a greedy multivariate Horner scheme
 //     P = v * Q + R,   v = the variable that saves the most multiplication work,  Q, R recursively
 // which needs 691 base-field multiplications per point for all 47 constraints of the Brainfuck AIR against 3 164
 // monomial by monomial (`profiles/microbench/horner_cost.py`).  The arithmetic follows the FIELD each operand lives
 // in: base columns reach this step lifted into the extension field with zero upper planes (every Table.extend:
 // `[xfield.lift(c) for c in codeword]`), so acc * variable costs 1 (both base-field), 3 (one of them) or 9
-// multiplications; the compiler tracks the accumulator's kind statically (Q_A / Q_S bits).
+// multiplications; the compiler tracks the kinds statically.
 //
 // The tree is flattened into a program for an accumulator + stack machine, children ordered by their stack need
-// (Sethi-Ullman), so the depth is <= log2(monomials) + 1 (3 for this AIR).  Every variable a constraint uses is
-// staged in shared memory once ([word][thread]: all its global loads are in flight together) and the stack lives
-// behind them; a constraint with more than Q_MAX_WORDS words reads its variables from global memory instead (Q_D).
+// (Sethi-Ullman), so the depth is <= log2(monomials) + 1 (3 for this AIR); the stack lives in shared memory as
+// [word][point of the thread][thread].  K points per thread share the decoding of every instruction.
 //
 // Montgomery multiplications by PLAIN codeword values: every factor divides the running value by 2^64, which the
 // host has compensated by scaling each monomial's coefficient with 2^(64 * degree) -- a leaf passes through
 // exactly `degree` multiplications on its way to the root.
+template <int K>
 __global__ void __launch_bounds__(Q_THREADS)
     quotient_kernel(const u64 *__restrict__ cw, u64 N, u32 width, u64 shift, const u64 *__restrict__ consts,
-                    const u32 *__restrict__ prog, const u32 *__restrict__ prog_off, const u64 *__restrict__ zinv,
+                    const u64 *__restrict__ prog, const u32 *__restrict__ prog_off, const u64 *__restrict__ zinv,
                     u64 *__restrict__ out) {
     extern __shared__ u64 q_sm[];
-    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 i0 = (u64)blockIdx.x * (K * Q_THREADS) + threadIdx.x;  // point k of the thread: i0 + k * Q_THREADS
     const u32 c = blockIdx.y;
-    if (i >= N) return;
-    u64 inext = i + shift;
-    if (inext >= N) inext -= N;
-    const u64 *here = cw + i, *next = cw + inext - (u64)3 * width * N;
+    if (K == 1 && i0 >= N) return;  // K > 1 is only launched on domains that fill every thread
     struct Mem {
         u64 *mine;
-        const u64 *here, *next;
+        const u64 *here[K], *next[K];
         u64 N;
         u32 width;
-        __device__ __forceinline__ u64 var(u32 v, int j) const { return ((v >= width ? next : here) + ((u64)3 * v + j) * N)[0]; }
-        __device__ __forceinline__ u64 get(u32 w) const { return mine[w * Q_THREADS]; }
-        __device__ __forceinline__ void put(u32 w, u64 x) { mine[w * Q_THREADS] = x; }
-    } mem = {q_sm + threadIdx.x, here, next, N, width};
-    const u32 *pc = q_stage(prog + prog_off[c], mem);
-    const xfe acc = q_run(pc, consts, mem);
-    const u64 zm = zinv[i];
-    u64 *o = out + (u64)3 * c * N + i;
-    o[0] = lcanon(mont_mul(acc.c[0], zm));
-    o[N] = lcanon(mont_mul(acc.c[1], zm));
-    o[2 * N] = lcanon(mont_mul(acc.c[2], zm));
+        __device__ __forceinline__ u64 var(u32 v, int j, int k) const {
+            return ((v >= width ? next[k] : here[k]) + ((u64)3 * v + j) * N)[0];
+        }
+        __device__ __forceinline__ u64 get(u32 w, int k) const { return mine[(w * K + k) * Q_THREADS]; }
+        __device__ __forceinline__ void put(u32 w, int k, u64 x) { mine[(w * K + k) * Q_THREADS] = x; }
+    } mem;
+    mem.mine = q_sm + threadIdx.x;
+    mem.N = N;
+    mem.width = width;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const u64 i = i0 + (u64)k * Q_THREADS;
+        u64 inext = i + shift;
+        if (inext >= N) inext -= N;
+        mem.here[k] = cw + i;
+        mem.next[k] = cw + inext - (u64)3 * width * N;
+    }
+    xfe acc[K];
+    q_run<K>(prog + prog_off[c], consts, mem, acc);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const u64 i = i0 + (u64)k * Q_THREADS;
+        const u64 zm = zinv[i];
+        u64 *o = out + (u64)3 * c * N + i;
+        o[0] = lcanon(mont_mul(acc[k].c[0], zm));
+        o[N] = lcanon(mont_mul(acc[k].c[1], zm));
+        o[2 * N] = lcanon(mont_mul(acc[k].c[2], zm));
+    }
 }
 
 }  // namespace
@@ -185,31 +199,29 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
         cudaFreeAsync(d_kinds, st);
     }
     // compile (quotient_prog.h): expanded monomials -> greedy Horner tree -> stack program; one blob per call:
-    //     constants (3 words each) | zero flag, pad | prog_off | programs
-    std::vector<u64> consts;
-    std::vector<u32> code, prog_off;
-    u32 max_words = 0;
-    static const bool stage = !(getenv("B2S_Q_STAGE") && atoi(getenv("B2S_Q_STAGE")) == 0);
+    //     constants (3 words each) | zero flag, pad | programs (64-bit instructions) | prog_off
+    std::vector<u64> consts, code;
+    std::vector<u32> prog_off;
+    u32 max_need = 0;
     char why[160];
-    if (q_compile(width, n_constraints, h_mono_off, h_coeffs, h_factors, max_factors, kinds, stage, consts, code, prog_off,
-                  max_words, why, sizeof(why))) {
+    if (q_compile(width, n_constraints, h_mono_off, h_coeffs, h_factors, max_factors, kinds, consts, code, prog_off, max_need,
+                  why, sizeof(why))) {
         b2s_set_error("quotients: %s", why);
         return B2S_ERR_ARG;
     }
     const size_t n_coef = consts.size();
-    std::vector<u64> blob(n_coef + 1 + ((size_t)(n_constraints + 1) + code.size() + 1) / 2 + 1, 0);
+    std::vector<u64> blob(n_coef + 1 + code.size() + (n_constraints + 2) / 2, 0);
     memcpy(blob.data(), consts.data(), sizeof(u64) * n_coef);
-    u32 *words32 = reinterpret_cast<u32 *>(blob.data() + n_coef + 1);
-    memcpy(words32, prog_off.data(), sizeof(u32) * (n_constraints + 1));
-    memcpy(words32 + (n_constraints + 1), code.data(), sizeof(u32) * code.size());
+    memcpy(blob.data() + n_coef + 1, code.data(), sizeof(u64) * code.size());
+    memcpy(blob.data() + n_coef + 1 + code.size(), prog_off.data(), sizeof(u32) * (n_constraints + 1));
     u64 *d_blob = nullptr, *d_zinv = nullptr;
     B2S_CUDA(cudaMallocAsync(&d_blob, sizeof(u64) * blob.size(), st));
     B2S_CUDA(cudaMallocAsync(&d_zinv, sizeof(u64) * N, st));
     B2S_CUDA(cudaMemcpyAsync(d_blob, blob.data(), sizeof(u64) * blob.size(), cudaMemcpyHostToDevice, st));
     const u64 *d_coef = d_blob;
     int *d_flag = reinterpret_cast<int *>(d_blob + n_coef);
-    const u32 *d_poff = reinterpret_cast<const u32 *>(d_blob + n_coef + 1);
-    const u32 *d_code = d_poff + (n_constraints + 1);
+    const u64 *d_code = d_blob + n_coef + 1;
+    const u32 *d_poff = reinterpret_cast<const u32 *>(d_code + code.size());
     ZeroParams Z;
     u64 sq = omega;
     for (int b = 0; b < 32; ++b) {
@@ -231,12 +243,20 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
     else
         zerofier_kernel<1><<<(unsigned)((T + 255) / 256), 256, 0, st>>>(Z, T, d_zinv, d_flag);
     B2S_LAUNCHED();
-    const size_t smem = sizeof(u64) * Q_THREADS * (size_t)std::max<u32>(max_words, 1);
-    if (smem > 48 * 1024)  // per device and cheap: no caching across calls
-        B2S_CUDA(cudaFuncSetAttribute(quotient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    quotient_kernel<<<dim3((unsigned)((N + Q_THREADS - 1) / Q_THREADS), n_constraints), Q_THREADS, smem, st>>>(
-        d_cw, N, width, shift, d_coef, d_code, d_poff, d_zinv, d_out);
-    B2S_LAUNCHED();
+    // points per thread: 2 once the domain fills the machine twice over (env B2S_Q_K overrides: 1 or 2; 4 measured no faster)
+    static const int k_env = getenv("B2S_Q_K") ? atoi(getenv("B2S_Q_K")) : 0;
+    int QK = k_env ? k_env : (N >= ((u64)1 << 16) ? 2 : 1);
+    if (N < (u64)QK * Q_THREADS || (QK != 1 && QK != 2)) QK = 1;
+    const size_t smem = sizeof(u64) * Q_THREADS * 3 * (size_t)std::max<u32>(max_need, 1) * QK;
+    const dim3 grid((unsigned)((N + (u64)QK * Q_THREADS - 1) / ((u64)QK * Q_THREADS)), n_constraints);
+    auto launch = [&](auto kernel) -> int {
+        if (smem > 48 * 1024)  // per device and cheap: no caching across calls
+            B2S_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, Q_THREADS, smem, st>>>(d_cw, N, width, shift, d_coef, d_code, d_poff, d_zinv, d_out);
+        B2S_LAUNCHED();
+        return 0;
+    };
+    if (int rc = QK == 2 ? launch(quotient_kernel<2>) : launch(quotient_kernel<1>)) return rc;
     if (!h_zero_flag) {  // the caller has ruled a vanishing zerofier out: nothing to read back, the call stays asynchronous
         cudaFreeAsync(d_blob, st);
         cudaFreeAsync(d_zinv, st);

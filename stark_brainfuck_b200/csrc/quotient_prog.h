@@ -11,106 +11,119 @@
 #include "glmont.cuh"
 
 #define Q_THREADS 128
-#define Q_MAX_WORDS 96   // staged variable words + stack words per thread (1 KB of shared memory per word and CTA)
 #define Q_MAX_STACK 16
 
-// The constraint program (host-compiled, see b2s_quotients): one u32 per operation,
-//     opcode | Q_A (the accumulator holds an extension-field value) | Q_S (so does the operand) | Q_D | arg << 8
+// The constraint program (host-compiled, see q_compile): 64-bit instructions for an accumulator + stack machine.
+//   Q_START   [push the accumulator to stack[slot]]  then  acc = constant
+//   Q_STEP    [acc += stack[slot]]  [acc *= variable]  [acc += constant]      in this order
+//   Q_END
+// The kind of every operand (base-field value = upper coefficients zero, or extension-field value) is static and
+// travels in the instruction, so a multiplication costs 1, 3 or 9 base-field multiplications as the operands need.
 enum : u32 {
-    Q_LOADC = 0,   // acc = constant[arg]
-    Q_ADDC = 1,    // acc += constant[arg]
-    Q_MUL = 2,     // acc *= variable; arg = its first staged word, or with Q_D the variable's index (read from global)
-    Q_PUSH = 3,    // stack[arg] = acc
-    Q_ADDPOP = 4,  // acc += stack[arg]
-    Q_END = 5,
-    Q_A = 16,
-    Q_S = 32,
-    Q_D = 64,
-    Q_EXT_VAR = 0x80000000u,  // load-list word: the variable is a genuine extension-field column (three words)
+    Q_END = 0,
+    Q_START = 1,
+    Q_STEP = 2,
+    Q_FMT = 3,
+    Q_HAS_STACK = 1u << 2,  // START: push first; STEP: add the popped value first
+    Q_HAS_MUL = 1u << 3,
+    Q_HAS_ADDC = 1u << 4,
+    Q_ACC_X = 1u << 5,    // the accumulator holds an extension-field value when it is pushed / multiplied
+    Q_VAR_X = 1u << 6,    // the variable is a genuine extension-field column
+    Q_CONST_X = 1u << 7,  // the constant has extension-field coefficients
+    Q_POP_X = 1u << 8,    // the popped value is an extension-field value
 };
-
+#define Q_SLOT_SHIFT 12   // 4 bits
+#define Q_VAR_SHIFT 16    // 24 bits
+#define Q_CONST_SHIFT 40  // 24 bits
 
 // ---- interpreter ---------------------------------------------------------------------------------------------
-// Mem: var(v, j) = coefficient j of variable v at this point (global memory), get(w) / put(w, x) = the thread's
-// word w of staged variables + stack (shared memory).
-template <class Mem>
-GL_HD const u32 *q_stage(const u32 *pc, Mem &mem) {
-    const u32 n_loads = *pc++;
-    u32 w = 0;
-#pragma unroll 4
-    for (u32 k = 0; k < n_loads; ++k) {
-        const u32 lw = pc[k], v = lw & 0xFFFFFF;
-        mem.put(w++, mem.var(v, 0));
-        if (lw & Q_EXT_VAR) {
-            mem.put(w++, mem.var(v, 1));
-            mem.put(w++, mem.var(v, 2));
-        }
-    }
-    return pc + n_loads;
-}
-
-template <class Mem>
-GL_HD xfe q_run(const u32 *pc, const u64 *consts, Mem &mem) {
-    xfe acc = {{0, 0, 0}};
+// K points per thread share the decoding of every instruction.  Mem: var(v, j, k) = coefficient j of variable v
+// at the thread's k-th point (global memory); get(w, k) / put(w, k, x) = word w of its stack (shared memory).
+template <int K, class Mem>
+GL_HD void q_run(const u64 *pc, const u64 *consts, Mem &mem, xfe (&acc)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = xfe{{0, 0, 0}};
     for (;;) {
-        const u32 op = *pc++;
-        const u32 arg = op >> 8;
-        const u32 code = op & 15;
-        if (code == Q_MUL) {
-            u64 x0, x1 = 0, x2 = 0;
-            if (op & Q_D) {
-                x0 = mem.var(arg, 0);
-                if (op & Q_S) {
-                    x1 = mem.var(arg, 1);
-                    x2 = mem.var(arg, 2);
-                }
-            } else {
-                x0 = mem.get(arg);
-                if (op & Q_S) {
-                    x1 = mem.get(arg + 1);
-                    x2 = mem.get(arg + 2);
+        const u64 op = *pc++;
+        const u32 lo = (u32)op;
+        const u32 fmt = lo & Q_FMT;
+        const u32 hi = (u32)(op >> 32);
+        if (fmt == Q_STEP) {
+            if (lo & Q_HAS_STACK) {
+                const u32 w = 3 * ((lo >> Q_SLOT_SHIFT) & 15);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    acc[k].c[0] = ladd(acc[k].c[0], mem.get(w, k));
+                    if (lo & Q_POP_X) {
+                        acc[k].c[1] = ladd(acc[k].c[1], mem.get(w + 1, k));
+                        acc[k].c[2] = ladd(acc[k].c[2], mem.get(w + 2, k));
+                    }
                 }
             }
-            if (!(op & Q_S)) {
-                acc.c[0] = mont_mul(acc.c[0], x0);
-                if (op & Q_A) {
-                    acc.c[1] = mont_mul(acc.c[1], x0);
-                    acc.c[2] = mont_mul(acc.c[2], x0);
+            if (lo & Q_HAS_MUL) {
+                const u32 v = (u32)(op >> Q_VAR_SHIFT) & 0xFFFFFF;  // bits 16 .. 39
+                if (!(lo & Q_VAR_X)) {
+                    u64 x[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) x[k] = mem.var(v, 0, k);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        acc[k].c[0] = mont_mul(acc[k].c[0], x[k]);
+                        if (lo & Q_ACC_X) {
+                            acc[k].c[1] = mont_mul(acc[k].c[1], x[k]);
+                            acc[k].c[2] = mont_mul(acc[k].c[2], x[k]);
+                        }
+                    }
+                } else {
+                    xfe x[K];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) x[k] = xfe{{mem.var(v, 0, k), mem.var(v, 1, k), mem.var(v, 2, k)}};
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        if (!(lo & Q_ACC_X)) {  // base-field value times an extension-field variable
+                            const u64 a = acc[k].c[0];
+                            acc[k].c[0] = mont_mul(a, x[k].c[0]);
+                            acc[k].c[1] = mont_mul(a, x[k].c[1]);
+                            acc[k].c[2] = mont_mul(a, x[k].c[2]);
+                        } else {
+                            acc[k] = x_mul_mont(acc[k], x[k]);
+                        }
+                    }
                 }
-            } else if (!(op & Q_A)) {  // base-field value times an extension-field variable
-                const u64 a = acc.c[0];
-                acc.c[0] = mont_mul(a, x0);
-                acc.c[1] = mont_mul(a, x1);
-                acc.c[2] = mont_mul(a, x2);
-            } else {
-                acc = x_mul_mont(acc, xfe{{x0, x1, x2}});
             }
-        } else if (code == Q_ADDC) {
-            const u64 *k = consts + 3 * (u64)arg;  // host-scaled constants are canonical
-            acc.c[0] = ladd(acc.c[0], k[0]);
-            if (op & Q_S) {
-                acc.c[1] = ladd(acc.c[1], k[1]);
-                acc.c[2] = ladd(acc.c[2], k[2]);
+            if (lo & Q_HAS_ADDC) {  // host-scaled constants are canonical
+                const u64 *cst = consts + 3 * (hi >> (Q_CONST_SHIFT - 32));
+                const u64 c0 = cst[0];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k].c[0] = ladd(acc[k].c[0], c0);
+                if (lo & Q_CONST_X) {
+                    const u64 c1 = cst[1], c2 = cst[2];
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        acc[k].c[1] = ladd(acc[k].c[1], c1);
+                        acc[k].c[2] = ladd(acc[k].c[2], c2);
+                    }
+                }
             }
-        } else if (code == Q_LOADC) {
-            const u64 *k = consts + 3 * (u64)arg;
-            acc.c[0] = k[0];
-            acc.c[1] = (op & Q_S) ? k[1] : 0;
-            acc.c[2] = (op & Q_S) ? k[2] : 0;
-        } else if (code == Q_PUSH) {
-            mem.put(arg, lcanon(acc.c[0]));
-            if (op & Q_A) {
-                mem.put(arg + 1, lcanon(acc.c[1]));
-                mem.put(arg + 2, lcanon(acc.c[2]));
+        } else if (fmt == Q_START) {
+            const u64 *cst = consts + 3 * (hi >> (Q_CONST_SHIFT - 32));
+            if (lo & Q_HAS_STACK) {
+                const u32 w = 3 * ((lo >> Q_SLOT_SHIFT) & 15);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    mem.put(w, k, lcanon(acc[k].c[0]));
+                    if (lo & Q_ACC_X) {
+                        mem.put(w + 1, k, lcanon(acc[k].c[1]));
+                        mem.put(w + 2, k, lcanon(acc[k].c[2]));
+                    }
+                }
             }
-        } else if (code == Q_ADDPOP) {
-            acc.c[0] = ladd(acc.c[0], mem.get(arg));
-            if (op & Q_S) {
-                acc.c[1] = ladd(acc.c[1], mem.get(arg + 1));
-                acc.c[2] = ladd(acc.c[2], mem.get(arg + 2));
-            }
+            const u64 c0 = cst[0];
+            const u64 c1 = (lo & Q_CONST_X) ? cst[1] : 0, c2 = (lo & Q_CONST_X) ? cst[2] : 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = xfe{{c0, c1, c2}};
         } else {
-            return acc;
+            return;
         }
     }
 }
@@ -133,10 +146,7 @@ struct QCompiler {
     u32 width;
     std::vector<QNode> nodes;
     std::vector<u64> &consts;  // three words per constant, shared by the call
-    std::vector<u32> code;
-    std::vector<u32> slot;  // per variable: first staged word, or ~0 (read from global)
-    u32 stack0 = 0;         // first stack word
-    bool direct = false;
+    std::vector<u64> code;
 
     QCompiler(u32 nv, const std::vector<u32> &k, u32 w, std::vector<u64> &cs) : n_vars(nv), kinds(k), width(w), consts(cs) {}
     bool var_base(u32 v) const { return kinds[v >= width ? v - width : v] != 0; }
@@ -189,54 +199,78 @@ struct QCompiler {
         nodes.push_back(n);
         return (int)nodes.size() - 1;
     }
-    // emits code that leaves the node's value in the accumulator; `sp` = stack slots in use; returns "is extension"
+    // ---- emission: a peephole over the parts  pop-add -> multiply -> add constant  of one Q_STEP
+    u64 pending = 0;  // Q_STEP under construction
+    void flush() {
+        if (pending) code.push_back(pending);
+        pending = 0;
+    }
+    void start(bool push, bool acc_ext, u32 slot, const QNode &leaf) {
+        flush();
+        code.push_back((u64)(Q_START | (push ? Q_HAS_STACK : 0u) | (push && acc_ext ? Q_ACC_X : 0u) | (leaf.ext ? Q_CONST_X : 0u)) |
+                       ((u64)slot << Q_SLOT_SHIFT) | ((u64)leaf.cidx << Q_CONST_SHIFT));
+    }
+    void pop_add(u32 slot, bool popped_ext) {
+        flush();  // always the first part of a step
+        pending = (u64)(Q_STEP | Q_HAS_STACK | (popped_ext ? Q_POP_X : 0u)) | ((u64)slot << Q_SLOT_SHIFT);
+    }
     bool mul(bool acc_ext, u32 v) {
+        if (pending & (u64)(Q_HAS_MUL | Q_HAS_ADDC)) flush();
+        if (!pending) pending = Q_STEP;
         const bool vx = !var_base(v);
-        const u32 arg = direct ? v : slot[v];
-        code.push_back(Q_MUL | (acc_ext ? Q_A : 0) | (vx ? Q_S : 0) | (direct ? Q_D : 0) | (arg << 8));
+        pending |= (u64)(Q_HAS_MUL | (acc_ext ? Q_ACC_X : 0u) | (vx ? Q_VAR_X : 0u)) | ((u64)v << Q_VAR_SHIFT);
         return acc_ext || vx;
     }
-    bool emit(int id, u32 sp) {
+    void add_const(const QNode &leaf) {
+        if (pending & (u64)Q_HAS_ADDC) flush();
+        if (!pending) pending = Q_STEP;
+        pending |= (u64)(Q_HAS_ADDC | (leaf.ext ? Q_CONST_X : 0u)) | ((u64)leaf.cidx << Q_CONST_SHIFT);
+    }
+    // emits code that leaves the node's value in the accumulator.  `sp` = stack slots in use; `push_first`: the
+    // accumulator holds a value (of kind push_ext) that must be saved to slot sp - 1 before it is overwritten --
+    // the save rides on the Q_START of the first leaf.  Returns "the value is an extension-field value".
+    bool emit(int id, u32 sp, bool push_first = false, bool push_ext = false) {
         const QNode &n = nodes[id];
         if (n.var < 0) {
-            code.push_back(Q_LOADC | (n.ext ? Q_S : 0) | (n.cidx << 8));
+            start(push_first, push_ext, push_first ? sp - 1 : 0, n);
             return n.ext;
         }
-        if (n.r < 0) return mul(emit(n.q, sp), (u32)n.var);
+        if (n.r < 0) return mul(emit(n.q, sp, push_first, push_ext), (u32)n.var);
         const QNode &r = nodes[n.r];
         if (r.var < 0) {
-            const bool a = mul(emit(n.q, sp), (u32)n.var);
-            code.push_back(Q_ADDC | (r.ext ? Q_S : 0) | (r.cidx << 8));
+            const bool a = mul(emit(n.q, sp, push_first, push_ext), (u32)n.var);
+            add_const(r);
             return a || r.ext;
         }
-        const u32 at = stack0 + 3 * sp;
         bool first, second;
         if (nodes[n.q].need >= r.need) {
-            first = mul(emit(n.q, sp), (u32)n.var);
-            code.push_back(Q_PUSH | (first ? Q_A : 0) | (at << 8));
-            second = emit(n.r, sp + 1);
+            first = mul(emit(n.q, sp, push_first, push_ext), (u32)n.var);
+            second = emit(n.r, sp + 1, true, first);
         } else {
-            first = emit(n.r, sp);
-            code.push_back(Q_PUSH | (first ? Q_A : 0) | (at << 8));
-            second = mul(emit(n.q, sp + 1), (u32)n.var);
+            first = emit(n.r, sp, push_first, push_ext);
+            second = mul(emit(n.q, sp + 1, true, first), (u32)n.var);
         }
-        code.push_back(Q_ADDPOP | (first ? Q_S : 0) | (at << 8));
+        pop_add(sp, first);
         return first || second;
     }
 };
 
-// Compiles every constraint of a call.  kinds[v] != 0: codeword v is a lifted base-field column.  stage: keep the
-// variables of a constraint in shared memory when they fit.  Returns 0, or 1 with a message in `why`.
+// Compiles every constraint of a call.  kinds[v] != 0: codeword v is a lifted base-field column.  prog_off[c] = first
+// instruction of constraint c in `code`; max_need = stack slots the deepest constraint uses.  Returns 0, or 1 with a
+// message in `why`.
 inline int q_compile(u32 width, u32 n_constraints, const u32 *h_mono_off, const u64 *h_coeffs, const u32 *h_factors,
-                     u32 max_factors, const std::vector<u32> &kinds, bool stage, std::vector<u64> &consts,
-                     std::vector<u32> &code, std::vector<u32> &prog_off, u32 &max_words, char *why, size_t why_len) {
+                     u32 max_factors, const std::vector<u32> &kinds, std::vector<u64> &consts, std::vector<u64> &code,
+                     std::vector<u32> &prog_off, u32 &max_need, char *why, size_t why_len) {
     const u32 n_vars = 2 * width;
     prog_off.assign(n_constraints + 1, 0);
-    max_words = 0;
+    max_need = 0;
+    if (n_vars >= (1u << 24)) {
+        snprintf(why, why_len, "too many variables (%u)", n_vars);
+        return 1;
+    }
     for (u32 c = 0; c < n_constraints; ++c) {
         prog_off[c] = (u32)code.size();
         std::vector<QMono> ms;
-        std::vector<unsigned char> used(n_vars, 0);
         for (u32 m = h_mono_off[c]; m < h_mono_off[c + 1]; ++m) {
             QMono q;
             q.e.assign(n_vars, 0);
@@ -245,7 +279,6 @@ inline int q_compile(u32 width, u32 n_constraints, const u32 *h_mono_off, const 
                 const u32 fac = h_factors[m * max_factors + f], e = fac & 0xFF, v = fac >> 8;
                 if (e == 0) continue;
                 q.e[v] += e;  // a variable listed twice multiplies twice
-                used[v] = 1;
                 degree += e;
             }
             const u64 r = gl_pow(GL_EPS, degree);  // 2^64 = EPS (mod p)
@@ -265,31 +298,14 @@ inline int q_compile(u32 width, u32 n_constraints, const u32 *h_mono_off, const 
             snprintf(why, why_len, "constraint %u needs an evaluation stack of %u entries (limit %u)", c, need, Q_MAX_STACK);
             return 1;
         }
-        // stage the constraint's variables in shared memory when they fit next to the stack
-        qc.slot.assign(n_vars, 0xFFFFFFFFu);
-        std::vector<u32> loads;
-        u32 words = 0;
-        for (u32 v = 0; v < n_vars; ++v)
-            if (used[v]) {
-                qc.slot[v] = words;
-                words += qc.var_base(v) ? 1 : 3;
-                loads.push_back(v | (qc.var_base(v) ? 0 : Q_EXT_VAR));
-            }
-        if (!stage || words + 3 * need > Q_MAX_WORDS) {
-            qc.direct = true;
-            loads.clear();
-            words = 0;
-        }
-        qc.stack0 = words;
-        max_words = std::max(max_words, words + 3 * need);
-        code.push_back((u32)loads.size());
-        code.insert(code.end(), loads.begin(), loads.end());
+        max_need = std::max(max_need, need);
         qc.emit(root, 0);
+        qc.flush();
         qc.code.push_back(Q_END);
         code.insert(code.end(), qc.code.begin(), qc.code.end());
     }
     prog_off[n_constraints] = (u32)code.size();
-    if (consts.size() / 3 >= (1u << 24) || n_vars >= (1u << 24)) {
+    if (consts.size() / 3 >= (1u << 24)) {
         snprintf(why, why_len, "program too large (%zu constants)", consts.size() / 3);
         return 1;
     }
