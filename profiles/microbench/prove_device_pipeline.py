@@ -1,8 +1,9 @@
 """Device-time budget of one BrainfuckStark.prove at BASELINE config 5's size (trace padded to 2^16, FRI domain
 2^20) with SYNTHETIC traces: the device ops the drop-in issues for a proof, in order, with the real constraint
 programs of the reference's AIR (tests/golden/air.json).  Not a benchmark contract; it answers "how much of a
-proof is device time".  Salted trees are stood in for by field-leaf trees over one plane triple per tree
-(their real leaves are host-pickled tuples).  Run on a GPU box: python profiles/microbench/prove_device_pipeline.py"""
+proof is device time".  The two salted trees hash the real row leaves (17- and 10-tuples, templates derived from
+the mirror's classes as the glue derives them from a proof's sample row).
+Run on a GPU box: python profiles/microbench/prove_device_pipeline.py"""
 import json
 import os
 import sys
