@@ -90,7 +90,8 @@ class DistCodeword(DeviceCodeword):
         self._df = df
         self._layout = layout
         self._local = local_planes  # slot -> (3, blk) device tensor (None on ranks that own nothing)
-        self._xfield = xfield
+        self._field = xfield
+        self.kind, self._base = "x", None
         self._n = layout.n
         self._cache = {}
 

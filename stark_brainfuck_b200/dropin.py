@@ -45,6 +45,23 @@ def current_glue():
 _COMB_BEGIN = "# compute terms of nonlinear combination polynomial"
 _COMB_END = "# commit to combination codeword"
 _COMB_HOOK = "__b2s_combination__"
+_ROWS_HOOK = "__b2s_rows__"
+# the two transpositions of prove() (code/brainfuck_stark.py:178, :196): rows of codewords for the salted trees
+_ROWS_STATEMENTS = ("zipped_codeword = list(zip(*all_base_codewords))",
+                    "zipped_extension_codeword = list(zip(*extension_codewords))")
+# last statement of ProcessorTable / InstructionTable / MemoryTable.extend and IOTable.extend_iotable
+_LIFT_STATEMENT = "self.codewords = [[xfield.lift(c) for c in cdwd]"
+
+
+def lazy_rows_source(src):
+    """prove() source with `list(zip(*codewords))` routed through the rows hook (which returns the same list unless
+    the codewords are device views).  A statement that is not where this reference version has it stays as it is:
+    zip then iterates the device views, which materialises them -- slower, same result."""
+    for stmt in _ROWS_STATEMENTS:
+        if src.count(stmt) == 1:
+            name, arg = stmt.split(" = list(zip(*")
+            src = src.replace(stmt, "%s = %s(%s)" % (name, _ROWS_HOOK, arg.rstrip(")")))
+    return src
 
 
 def guarded_prove_source(prove):
@@ -63,15 +80,17 @@ def guarded_prove_source(prove):
     call = (pad + "combination_codeword = " + _COMB_HOOK + "(self.fri.domain, self.xfield, self.max_degree, "
             "randomizer_codeword, base_codewords, base_degree_bounds, extension_codewords, extension_degree_bounds, "
             "quotient_codewords, quotient_degree_bounds, weights)\n" + pad + "if combination_codeword is None:\n")
-    return src[:a] + call + textwrap.indent(block, "    ") + src[b:]
+    return lazy_rows_source(src[:a] + call + textwrap.indent(block, "    ") + src[b:])
 
 
-def install(reference_dir=None, engine=None, quotients=True, salted=True, combination=True, lde=True):
+def install(reference_dir=None, engine=None, quotients=True, salted=True, combination=True, lde=True, lazy=None):
     """Patch the reference modules importable from `reference_dir` (or already on sys.path).
     `quotients=True` also moves the quotient-codeword loops of table.py / permutation_argument.py
     (93 % of prove()) to the device, `salted=True` the trees of salted_merkle.py,
     `combination=True` the nonlinear combination inside BrainfuckStark.prove (see module docstring),
     `lde=True` Table.interpolate_columns / lde / ldex as batched transforms over all columns of a table.
+    `lazy` (default: on unless B2S_LAZY_CODEWORDS=0): inside prove() the codewords of lde / ldex / xevaluate are device
+    views whose elements are built on first access (glue.DeviceCodeword); needs quotients, salted, combination and lde.
     Returns the Glue in use."""
     global _state
     if _state is not None:
@@ -85,6 +104,9 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
                            "default protocol is %d" % pickle.DEFAULT_PROTOCOL)
     if reference_dir is not None and reference_dir not in sys.path:
         sys.path.insert(0, reference_dir)
+    if lazy is None:
+        lazy = os.environ.get("B2S_LAZY_CODEWORDS", "1") != "0"
+    lazy = bool(lazy and quotients and salted and combination and lde) and os.environ.get("DEBUG") is None
     mods = {name: importlib.import_module(name)
             for name in ("algebra", "univariate", "extension_field", "ntt", "merkle", "ip", "fri")}
     binding = Binding.from_modules(mods["algebra"], mods["univariate"], mods["extension_field"])
@@ -191,6 +213,47 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
         set_attr(T, "lde", lde_)
         set_attr(T, "ldex", ldex_)
 
+    # -- 5c. Table.extend ends in `self.codewords = [[xfield.lift(c) for c in cdwd] for cdwd in self.codewords]`
+    # (e.g. code/io_table.py:106-107): 2.1 M lift calls in a Hello-World proof for lists only the quotient kernels
+    # read.  With device views as codewords the statement runs over an empty list and the glue lifts the views.
+    if lazy:
+        from .glue import DeviceCodeword
+        XField = binding.ExtensionField
+
+        def lifting(orig):
+            def extend(self, *args, **kwargs):
+                codewords = getattr(self, "codewords", None)
+                if not glue._lazy or type(codewords) is not list or \
+                        not any(type(c) is DeviceCodeword for c in codewords):
+                    return orig(self, *args, **kwargs)
+                self.codewords = []
+                try:
+                    result = orig(self, *args, **kwargs)
+                    as_expected = self.codewords == [] and type(self.field) is XField
+                finally:
+                    self.codewords = codewords
+                if not as_expected:  # ruled out by the source check at install time
+                    raise RuntimeError("Table.extend did not treat its codewords as this reference version does")
+                self.codewords = glue.lift_codewords(self.field, codewords)
+                return result
+            extend.__wrapped__ = orig
+            return extend
+        for mod_name, cls_name, meth in (("processor_table", "ProcessorTable", "extend"),
+                                         ("instruction_table", "InstructionTable", "extend"),
+                                         ("memory_table", "MemoryTable", "extend"),
+                                         ("io_table", "IOTable", "extend_iotable")):
+            try:
+                cls = getattr(importlib.import_module(mod_name), cls_name)
+                orig = cls.__dict__[meth]
+                src = inspect.getsource(orig)
+                if src.count(_LIFT_STATEMENT) != 1 or src.count("codewords") != 2:
+                    raise LookupError("%s.%s has an unexpected shape" % (cls_name, meth))
+                set_attr(cls, meth, lifting(orig))
+            except (ImportError, KeyError, LookupError, OSError, TypeError) as e:
+                lazy = False  # without the wrapper a device view would be lifted element by element: no gain
+                warnings.warn("codewords stay host lists inside prove(): %s" % e)
+                break
+
     # -- 6. next row: the nonlinear combination inside BrainfuckStark.prove -------
     if combination:
         try:
@@ -203,13 +266,16 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
             # DEBUG keeps the reference's own block (it prints and asserts degree bounds on the way)
             bs.__dict__[_COMB_HOOK] = lambda *args: (None if os.environ.get("DEBUG") is not None
                                                      else glue.combination_codeword(*args))
+            saved["globals"].append((bs, _ROWS_HOOK, bs.__dict__.get(_ROWS_HOOK, _MISSING)))
+            bs.__dict__[_ROWS_HOOK] = glue.rows_of
             guarded = scope["prove"]
+            lazy_views = lazy
 
             def prove(self, *args, **kwargs):
                 # codewords stay readable on the device for the length of one proof; the cyclic collector is paused:
                 # a proof allocates tens of millions of acyclic element objects and every generation-0 overflow
                 # would rescan them (marshal.bulk_allocation)
-                with glue.keep_planes(), bulk_allocation():
+                with glue.keep_planes(lazy=lazy_views and os.environ.get("DEBUG") is None), bulk_allocation():
                     return guarded(self, *args, **kwargs)
             prove.__wrapped__ = guarded
             prove.__doc__ = guarded.__doc__

@@ -30,6 +30,7 @@ class Glue:
         self._xtpl = {}  # id(xfield) -> (xfield, templates)
         self._btpl = {}  # id(field)  -> (field, templates)
         self._kept = None  # id(list) -> (list, device planes, probe positions, probe elements) inside keep_planes()
+        self._lazy = False  # inside keep_planes(lazy=True): codewords are handed out as DeviceCodewords
         self.coset_routed = 0  # evaluate_domain calls that became one coset transform
 
     @property
@@ -68,6 +69,8 @@ class Glue:
 
     def _to_device(self, values):
         """list of field elements -> (device planes, kind, field object for the results)"""
+        if type(values) is DeviceCodeword and values.kind in "xb":
+            return values._planes, values.kind, values._field
         first = values[0]
         if self.B.is_xfe(first):
             return self.engine.upload(self.B.xfe_to_np(values)), "x", first.field
@@ -75,7 +78,9 @@ class Glue:
             return self.engine.upload(self.B.bfe_to_np(values)), "b", first.field
         raise TypeError("cannot transform a list of %r" % type(first))
 
-    def _from_device(self, t, kind, field, keep=False):
+    def _from_device(self, t, kind, field, keep=False, lazy=False):
+        if lazy and self._lazy and self._kept is not None:
+            return DeviceCodeword(self, t, field, kind)
         a = self.engine.download(t)
         values = self.B.np_to_xfe(a, field) if kind == "x" else self.B.np_to_bfe(a[0], field)
         if keep:  # a codeword that a later device op (nonlinear combination) can read without marshalling
@@ -87,12 +92,17 @@ class Glue:
     # keep_planes() -- the drop-in opens it around BrainfuckStark.prove, whose code is known not to
     # mutate its codewords in place -- and holds the lists strongly, so ids cannot be recycled.
     @contextlib.contextmanager
-    def keep_planes(self):
+    def keep_planes(self, lazy=False):
+        """lazy=True (the drop-in's BrainfuckStark.prove): lde / ldex / Domain.xevaluate hand their codewords out as
+        DeviceCodewords -- list-like views whose elements are built on first access.  A proof reads a few hundred
+        rows of the 46 codewords it makes (the openings); building every element object is most of its host time."""
         outer, self._kept = self._kept, {}
+        outer_lazy, self._lazy = self._lazy, bool(lazy)
         try:
             yield self
         finally:
             self._kept = outer
+            self._lazy = outer_lazy
 
     def remember_planes(self, values, planes):
         if self._kept is not None and len(values):
@@ -144,7 +154,8 @@ class Glue:
         return ent[1]
 
     # ------------------------------------------------------------------ code/ntt.py
-    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None, lone_source=None, res_field=None):
+    def _transform(self, primitive_root, values, inverse, offset=1, n_out=None, lone_source=None, res_field=None,
+                   lazy=False):
         n = len(values) if n_out is None else n_out
         w = self.base_value(primitive_root, "primitive_root")
         # every 2-power root of unity of F_p^3 lies in F_p, so a root with higher
@@ -172,7 +183,7 @@ class Glue:
             X = self.B.ExtensionFieldElement
             values = [X(base[i % share].polynomial, res_field) for i in range(n)]
         else:
-            return self._from_device(out, kind, res_field, keep=True)
+            return self._from_device(out, kind, res_field, keep=True, lazy=lazy)
         self.remember_planes(values, out)  # the values are the device's either way; only the identities differ
         return values
 
@@ -226,7 +237,7 @@ class Glue:
         assert n >= 2 and pow(w, n // 2, P) != 1, "supplied root is not primitive root of supplied order"
         return self._transform(primitive_root, values, True)
 
-    def fast_coset_evaluate(self, polynomial, offset, generator, order):
+    def fast_coset_evaluate(self, polynomial, offset, generator, order, lazy=False):
         """code/ntt.py:164-168: scale by offset, zero-pad to `order`, ntt -- one fused call"""
         coeffs = polynomial.coefficients
         m = len(coeffs)
@@ -248,7 +259,7 @@ class Glue:
             lone = (offset ^ 0) * coeffs[0]  # the scaled constant term, built by the caller's own classes
         # the scaled coefficients (offset ^ i) * c carry offset.field (code/univariate.py:169), ntt keeps it
         return self._transform(generator, coeffs, False, offset=off, n_out=order, lone_source=lone,
-                               res_field=offset.field)
+                               res_field=offset.field, lazy=lazy)
 
     def fast_coset_interpolate(self, offset, generator, values):
         """code/ntt.py:171-174: intt, then scale by offset^-1; all n coefficients are kept"""
@@ -372,14 +383,15 @@ class Glue:
             raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
         out = self.engine.ntt(d, _ilog2(n), w, offset=off)
         # scaled coefficients take offset.field (code/univariate.py:169); ntt keeps values[0].field
-        return self._from_device(out, kind, dom.offset.field if kind == "b" else coeffs[0].field, keep=True)
+        return self._from_device(out, kind, dom.offset.field if kind == "b" else coeffs[0].field, keep=True, lazy=True)
 
     def domain_xevaluate(self, dom, polynomial, xfield=None):
         """code/fri.py:32-37"""
         if xfield is None:
             assert len(polynomial.coefficients) != 0, "trying to xevaluate zero polynomial with no target field"
             xfield = polynomial.coefficients[0].field
-        return self.fast_coset_evaluate(polynomial, xfield.lift(dom.offset), xfield.lift(dom.omega), dom.length)
+        return self.fast_coset_evaluate(polynomial, xfield.lift(dom.offset), xfield.lift(dom.omega), dom.length,
+                                        lazy=True)
 
     def domain_interpolate(self, dom, values):
         """code/fri.py:39-40"""
@@ -506,25 +518,45 @@ class Glue:
             raise AttributeError("'ExtensionFieldElement' object has no attribute 'value'")
         if xfield is not None and kind == "b":
             raise AttributeError("'BaseFieldElement' object has no attribute 'polynomial'")
-        coeffs = eng.download(buf)
+        coeffs = eng.download(buf) if kind == "x" else None
         out = eng.ntt(buf, _ilog2(N), domain.omega.value, offset=domain.offset.value)
-        a = eng.download(out)
+        lazy = self._lazy and self._kept is not None
+        a = None if lazy else eng.download(out)
         res = []
         for c in range(len(columns)):
             if kind == "b":
-                values = B.np_to_bfe(a[c], domain.offset.field)  # code/fri.py:26-30 via code/univariate.py:169
-                self.remember_planes(values, out[c:c + 1])
+                if lazy:
+                    values = DeviceCodeword(self, out[c:c + 1], domain.offset.field, "b")
+                else:
+                    values = B.np_to_bfe(a[c], domain.offset.field)  # code/fri.py:26-30 via code/univariate.py:169
+                    self.remember_planes(values, out[c:c + 1])
             else:
                 ca = coeffs[3 * c:3 * c + 3]
                 if self._shared_output_period(ca, N):
                     # sparse interpolants (constant columns) share coefficient objects between outputs in the
                     # reference's recursion: take the per-column path that models it (see _transform)
                     values = self.domain_xevaluate(domain, Pn(B.np_to_xfe(ca, first.field)), xfield)
+                elif lazy:
+                    values = DeviceCodeword(self, out[3 * c:3 * c + 3], xfield, "x")
                 else:
                     values = B.np_to_xfe(a[3 * c:3 * c + 3], xfield)  # scale by lift(offset): offset.field = xfield
                     self.remember_planes(values, out[3 * c:3 * c + 3])
             res.append(values)
         return res
+
+    def lift_codewords(self, xfield, codewords):
+        """`[[xfield.lift(c) for c in cdwd] for cdwd in codewords]`, the last statement of every Table.extend of the
+        reference (e.g. code/io_table.py:106-107).  A base-field DeviceCodeword becomes a lifted VIEW of itself (its
+        elements wrap the base codeword's own element objects, as lift does); anything else is lifted as written."""
+        return [DeviceCodeword(self, cw._planes, xfield, "l", base=cw) if type(cw) is DeviceCodeword and cw.kind == "b"
+                else [xfield.lift(c) for c in cw] for cw in codewords]
+
+    def rows_of(self, codewords):
+        """`list(zip(*codewords))` (code/brainfuck_stark.py:178, :196): rows built on first access when the codewords
+        are device views, the reference's own list otherwise"""
+        if self._lazy and self._kept is not None and codewords and any(type(c) is DeviceCodeword for c in codewords):
+            return LazyRows(self, codewords)
+        return list(zip(*codewords))
 
     # ------------------------------------------------------------------ code/table.py quotients
     def compile_constraints(self, constraints, n_vars):
@@ -568,6 +600,8 @@ class Glue:
         for j in range(width):
             planes = self.planes_of(codewords[j])
             lifted = self.lifted_planes_of(codewords[j]) if planes is None else None
+            if planes is not None and planes.shape[0] == 1 and type(codewords[j]) is DeviceCodeword:
+                planes, lifted = None, planes  # the lifted view of a base-field codeword (or the codeword itself)
             if planes is not None and planes.shape[0] == 3:
                 eng.copy(cw[j], planes)
             elif lifted is not None:  # a base-field codeword lifted element by element: c0 = the plane, c1 = c2 = 0
@@ -595,13 +629,18 @@ class Glue:
             return height <= 0 or N % height != 0
         return pow(int(omicron_inv), N, P) != 1
 
+    @staticmethod
+    def _element_field(codeword):
+        """codeword[0].field without building the element of a device view"""
+        return codeword._field if type(codeword) is DeviceCodeword else codeword[0].field
+
     def quotient_codewords(self, domain, codewords, width, constraints, kind, height=0, omicron_inv=1, shift=0):
         """code/table.py:155-178 / :190-236 / :253-286: [mpo.evaluate(point_i) * lift(zerofier_inverse[i])]
         for every constraint over the whole FRI domain, on the device."""
         N = domain.length
         n_vars = 2 * width if kind == ZEROFIER_TRANSITION else width
         program = self.compile_constraints(constraints, n_vars)
-        xfield = codewords[0][0].field  # acc = point[0].field.zero() (code/multivariate.py:106)
+        xfield = self._element_field(codewords[0])  # acc = point[0].field.zero() (code/multivariate.py:106)
         cw, base_columns = self._table_planes(codewords, width, N)
         out, vanishes = self.engine.quotients(cw, shift, *program, kind, height, omicron_inv, domain.offset.value,
                                               domain.omega.value, base_columns=base_columns,
@@ -686,7 +725,7 @@ class Glue:
         """code/permutation_argument.py:11-20: (lhs - rhs) * lift(1 / (x - 1)) as a two-variable program"""
         lhs = pa.all_tables[pa.lhs[0]].codewords[pa.lhs[1]]
         rhs = pa.all_tables[pa.rhs[0]].codewords[pa.rhs[1]]
-        xfield = lhs[0].field
+        xfield = self._element_field(lhs)
         difference = MPolynomial({(1, 0): xfield.one(), (0, 1): -xfield.one()})
         return self.quotient_codewords(fri_domain, [lhs, rhs], 2, [difference], ZEROFIER_BOUNDARY)[0]
 
@@ -748,11 +787,22 @@ class Glue:
             npo2 <<= 1
         tree.depth = _ilog2(npo2)  # code/salted_merkle.py:10-22 (0 leaves -> depth 0 as well)
         from .marshal import bulk_allocation
-        with bulk_allocation():
-            tree.leafs = [(element, urandom(24)) for element in data_array]  # code/salted_merkle.py:25
-        # code/salted_merkle.py:23: with no leaves the reference's own consistency assert fires
-        assert n != 0, "in SaltedMerkle.__init__, next_power_of_two = 0 =/= 1 << self.depth = 1"
-        nodes = self._row_tree(tree.leafs) if n == npo2 else None
+        nodes = None
+        if type(data_array) is LazyRows and n == npo2:
+            # rows of device codewords (prove() under the drop-in): the salts are drawn as the reference draws them,
+            # the (row, salt) pairs exist only for the leaves somebody opens
+            salts = [urandom(24) for _ in range(n)]  # code/salted_merkle.py:25
+            tree.leafs = LazyLeafs(data_array, salts, tree)
+            nodes = self._row_tree(data_array, salts)
+        if nodes is None:
+            with bulk_allocation():
+                if type(data_array) is LazyRows and n == npo2:
+                    tree.leafs = list(tree.leafs)  # same salts, rows materialised
+                else:
+                    tree.leafs = [(element, urandom(24)) for element in data_array]  # code/salted_merkle.py:25
+            # code/salted_merkle.py:23: with no leaves the reference's own consistency assert fires
+            assert n != 0, "in SaltedMerkle.__init__, next_power_of_two = 0 =/= 1 << self.depth = 1"
+            nodes = self._row_tree([leaf[0] for leaf in tree.leafs], [leaf[1] for leaf in tree.leafs]) if n == npo2 else None
         if nodes is None:  # rows the device templates cannot express: the host pickles, the device hashes
             dumps = pickle.dumps
             nodes = self.engine.merkle_blobs([dumps(e) + dumps(salt) for e, salt in tree.leafs])
@@ -767,16 +817,24 @@ class Glue:
         after checking that the whole column has ONE identity pattern (the row template assumes it)."""
         B, n = self.B, len(rows)
         first = rows[0]
-        if type(first) is not tuple or not first or any(type(r) is not tuple or len(r) != len(first) for r in rows):
+        lazy = type(rows) is LazyRows
+        if type(first) is not tuple or not first or \
+                (not lazy and any(type(r) is not tuple or len(r) != len(first) for r in rows)):
             return None
         planes = []
         for k, e in enumerate(first):
             ent = self._kept.get(("first", id(e))) if self._kept is not None else None
-            if ent is not None and len(ent[0]) == n and ent[1].shape[1] == n and \
+            if lazy and type(rows.columns[k]) is DeviceCodeword:
+                if rows.columns[k].kind == "l" or len(rows.columns[k]) != n:
+                    return None
+                col = rows.columns[k]._planes
+            elif ent is not None and len(ent[0]) == n and ent[1].shape[1] == n and \
                     all(rows[i][k] is v and ent[0][i] is v for i, v in zip(ent[2], ent[3])):
                 col = ent[1]
             else:
-                column = [r[k] for r in rows]
+                column = rows.columns[k] if lazy else [r[k] for r in rows]
+                if len(column) != n:
+                    return None
                 if B.is_bfe(e):
                     f = e.field
                     if not all(type(v) is B.BaseFieldElement and v.field is f for v in column):
@@ -791,16 +849,18 @@ class Glue:
             planes += [col[q] for q in range(col.shape[0])]
         return planes
 
-    def _row_tree(self, leafs):
+    def _row_tree(self, rows, salts):
         """Device tree over salted rows: the row pickle is a per-tree byte template
         derived from a sample row; the device splices the integers of the codeword planes and the salts.
-        Returns the node tensor, or None when the rows cannot be expressed (the caller then pickles)."""
+        rows: a list of tuples or LazyRows.  Returns the node tensor, or None when the rows cannot be expressed
+        (the caller then pickles)."""
         from . import marshal
-        n = len(leafs)
-        rows = [leaf[0] for leaf in leafs]
-        salt0 = leafs[0][1]
+        n = len(salts)
+        if n == 0 or len(rows) != n:
+            return None
+        salt0 = salts[0]
         frame = marshal.salt_frame(salt0) if type(salt0) is bytes else None
-        if frame is None or any(type(leaf[1]) is not bytes or len(leaf[1]) != len(salt0) for leaf in leafs):
+        if frame is None or any(type(x) is not bytes or len(x) != len(salt0) for x in salts):
             return None
         tpl = marshal.row_template(self.B, rows[0])
         if tpl is None:
@@ -809,7 +869,7 @@ class Glue:
         if planes is None or len(planes) != len(tpl.modes):
             return None
         eng = self.engine
-        salts = eng.upload_bytes(np.frombuffer(b"".join(leaf[1] for leaf in leafs), dtype=np.uint8).reshape(n, len(salt0)))
+        salts = eng.upload_bytes(np.frombuffer(b"".join(salts), dtype=np.uint8).reshape(n, len(salt0)))
         # a couple of rows rendered on the host as well: the template must reproduce the caller's pickler
         for i in {0, n // 2, n - 1}:
             t = tpl if marshal.row_signature(self.B, rows[i]) == tpl.signature else marshal.row_template(self.B, rows[i])
@@ -991,16 +1051,23 @@ ZEROFIER_BOUNDARY, ZEROFIER_TRANSITION, ZEROFIER_TERMINAL = 1, 2, 3
 
 
 class DeviceCodeword:
-    """A folded FRI codeword that lives on the device.  Behaves like the list of
-    ExtensionFieldElements the reference builds at code/fri.py:127-128 for the accesses the
-    reference makes (len, indexing, iteration); elements are materialised on demand and
-    cached, so repeated access returns the SAME object (pickle memoises by identity,
-    SURVEY B5 rule 3)."""
+    """A codeword that lives on the device.  Behaves like the list of field elements the reference builds (the
+    folded codewords of code/fri.py:127-128, the codewords of Table.lde / ldex, Domain.xevaluate) for the accesses
+    the reference makes -- len, indexing, slicing, iteration; elements are materialised on demand and cached, so
+    repeated access returns the SAME object (pickle memoises by identity, SURVEY B5 rule 3).
+    kind "x": ExtensionFieldElements of `field`, planes (3, n)
+         "b": BaseFieldElements of `field`, planes (1, n)
+         "l": `[xfield.lift(c) for c in base]` of a kind-"b" codeword `base` (what every Table.extend does to its
+              base codewords): element i wraps base[i] ITSELF as its only coefficient (none when it is zero,
+              code/extension_field.py:6-9, :113-116); planes = the base codeword's"""
 
-    def __init__(self, glue, planes, xfield):
+    def __init__(self, glue, planes, field, kind="x", base=None):
+        assert planes.shape[0] == (3 if kind == "x" else 1)
         self._glue = glue
         self._planes = planes
-        self._xfield = xfield
+        self._field = field
+        self.kind = kind
+        self._base = base
         self._n = planes.shape[1]
         self._cache = {}
 
@@ -1009,22 +1076,38 @@ class DeviceCodeword:
 
     def wanted(self, indices):
         """the indices that still have to be fetched (range-checked like list indexing)"""
-        need = [i for i in dict.fromkeys(indices) if i not in self._cache]
+        cache = self._cache if self.kind != "l" else self._base._cache
+        need = [i for i in dict.fromkeys(indices) if i not in cache]
         for i in need:
             if not 0 <= i < self._n:
                 raise IndexError("list index out of range")
         return need
 
     def fill(self, need, vals):
-        """vals: (len(need), 3) uint64 as gathered from the planes"""
-        mk, xf = self._glue.B.make_xfe, self._xfield
-        for i, v in zip(need, vals.tolist()):
-            self._cache[i] = mk(v[0], v[1], v[2], xf)
+        """vals: (len(need), number of planes) uint64 as gathered from the planes"""
+        B = self._glue.B
+        if self.kind == "x":
+            mk, xf = B.make_xfe, self._field
+            for i, v in zip(need, vals.tolist()):
+                self._cache[i] = mk(v[0], v[1], v[2], xf)
+        elif self.kind == "b":
+            for i, e in zip(need, B.np_to_bfe(vals[:, 0], self._field)):
+                self._cache[i] = e
+        else:
+            self._base.fill(need, vals)
 
     def prefetch(self, indices):
         need = self.wanted(indices)
         if need:
             self.fill(need, self._glue.engine.gather(self._planes, need))
+
+    def _lift(self, e):
+        B = self._glue.B
+        p = B.Polynomial.__new__(B.Polynomial)
+        p.__dict__ = {"coefficients": [e] if e.value != 0 else []}
+        x = B.ExtensionFieldElement.__new__(B.ExtensionFieldElement)
+        x.__dict__ = {"polynomial": p, "field": self._field}
+        return x
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -1032,7 +1115,12 @@ class DeviceCodeword:
         if i < 0:
             i += self._n
         if i not in self._cache:
-            self.prefetch([i])
+            if self.kind == "l":
+                if not 0 <= i < self._n:
+                    raise IndexError("list index out of range")
+                self._cache[i] = self._lift(self._base[i])
+            else:
+                self.prefetch([i])
         return self._cache[i]
 
     def __iter__(self):
@@ -1041,18 +1129,119 @@ class DeviceCodeword:
     def materialize(self):
         """the whole codeword as a real list (cached objects are reused)"""
         if len(self._cache) < self._n:
-            a = self._glue.engine.download(self._planes)
-            mk, xf = self._glue.B.make_xfe, self._xfield
-            c0, c1, c2 = a[0].tolist(), a[1].tolist(), a[2].tolist()
             from .marshal import bulk_allocation
+            B = self._glue.B
             with bulk_allocation():
-                for i in range(self._n):
-                    if i not in self._cache:
-                        self._cache[i] = mk(c0[i], c1[i], c2[i], xf)
+                if self.kind == "l":
+                    base = self._base.materialize()
+                    for i in range(self._n):
+                        if i not in self._cache:
+                            self._cache[i] = self._lift(base[i])
+                else:
+                    a = self._glue.engine.download(self._planes)
+                    fresh = B.np_to_xfe(a, self._field) if self.kind == "x" else B.np_to_bfe(a[0], self._field)
+                    for i in range(self._n):
+                        if i not in self._cache:
+                            self._cache[i] = fresh[i]
         return [self._cache[i] for i in range(self._n)]
 
     def __eq__(self, other):
         return list(self) == list(other)
+
+    __hash__ = None
+
+
+class LazyRows:
+    """`list(zip(*codewords))` over codewords of which some are DeviceCodewords (code/brainfuck_stark.py:178, :196):
+    row i is built on first access -- one device call gathers the row's elements from every device column -- and
+    cached, so the tuple the prover pushes twice is the same object twice."""
+
+    def __init__(self, glue, columns):
+        self._glue = glue
+        self.columns = list(columns)
+        self._n = min(len(c) for c in self.columns)  # zip stops at the shortest
+        self._cache = {}
+
+    def __len__(self):
+        return self._n
+
+    def prefetch(self, indices, tree=None):
+        """gather the elements of the given rows from every device column -- and, with `tree`, the authentication
+        paths of those leaves (SaltedMerkle.open follows leafs[i] in code/brainfuck_stark.py:316-326) -- with ONE
+        device call"""
+        sets, fills = [], []
+        for c in self.columns:
+            if type(c) is DeviceCodeword:
+                need = c.wanted(indices)
+                if need:
+                    for q in range(c._planes.shape[0]):
+                        sets.append((c._planes[q:q + 1], None, need))
+                    fills.append((c, need, c._planes.shape[0]))
+        nodes = getattr(tree, "nodes", None)
+        path_need = nodes.wanted_paths(indices, tree.depth) if type(nodes) is NodeView else []
+        if path_need:
+            sets.append((None, nodes._dev, path_need))
+        if not sets:
+            return
+        res = self._glue.engine.open_multi(sets)
+        k = 0
+        for c, need, q in fills:
+            c.fill(need, np.concatenate([res[k + j][0] for j in range(q)], axis=1))
+            k += q
+        if path_need:
+            nodes.fill_paths(path_need, res[k][1], tree.depth)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError("list index out of range")
+        row = self._cache.get(i)
+        if row is None:
+            self.prefetch([i])
+            row = self._cache[i] = tuple(c[i] for c in self.columns)
+        return row
+
+    def __iter__(self):
+        cols = [c.materialize() if type(c) is DeviceCodeword else c for c in self.columns]
+        for i in range(self._n):
+            row = self._cache.get(i)
+            if row is None:
+                row = self._cache[i] = tuple(c[i] for c in cols)
+            yield row
+
+
+class LazyLeafs:
+    """SaltedMerkle.leafs = [(element, salt)] (code/salted_merkle.py:25) over LazyRows: pairs built on first access
+    and cached; the salts are the objects drawn at construction"""
+
+    def __init__(self, rows, salts, tree=None):
+        self.rows, self.salts, self._tree = rows, salts, tree
+        self._cache = {}
+
+    def __len__(self):
+        return len(self.salts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self.salts)))]
+        if i < 0:
+            i += len(self.salts)
+        leaf = self._cache.get(i)
+        if leaf is None:
+            if 0 <= i < len(self.salts) and type(self.rows) is LazyRows:
+                self.rows.prefetch([i], self._tree)
+            leaf = self._cache[i] = (self.rows[i], self.salts[i])
+        return leaf
+
+    def __iter__(self):
+        for i, row in enumerate(self.rows):
+            leaf = self._cache.get(i)
+            if leaf is None:
+                leaf = self._cache[i] = (row, self.salts[i])
+            yield leaf
 
 
 class NodeView:

@@ -397,6 +397,90 @@ def case_lde(env, glue, make_table=None):
         glue.table_interpolate_columns(t, dom.omega, N // 2, range(1), seeded_urandom(1))
 
 
+def case_lazy_codewords(env, glue):
+    """The device views BrainfuckStark.prove() works on under the drop-in (glue.keep_planes(lazy=True)): lde / ldex /
+    Domain.xevaluate return DeviceCodewords whose elements, rows and lifted views are built on first access -- same
+    values, same pickles (tests/golden/lde.json), same objects on repeated access -- and the salted tree over their
+    rows equals the tree over the materialised rows."""
+    from stark_brainfuck_b200.glue import DeviceCodeword, LazyLeafs, LazyRows
+    g = golden("lde.json")
+    N = g["N"]
+    dom = env.Fri.Domain(env.field(g["offset"]), env.field(g["omega"]), N)
+    seen = 0
+    for c in g["cases"]:
+        h, bw, fw = c["height"], c["base_width"], c["full_width"]
+        if not h:
+            continue
+        t = types.SimpleNamespace(field=env.field, base_width=bw, full_width=fw, length=c["length"], height=h,
+                                  num_randomizers=c["num_randomizers"], omicron=env.field(c["omicron"]))
+        base = [[env.BaseFieldElement(v, env.field) for v in row] for row in c["base"]]
+        ext = [[X(env, *v) for v in row] for row in c["ext"]]
+        draw = seeded_urandom(c["urandom_seed"])
+        t.matrix = [list(row) for row in base]
+        with glue.keep_planes(lazy=True):
+            base_cw = glue.table_lde(t, dom, draw)
+            assert all(type(cw) is DeviceCodeword and cw.kind == "b" and len(cw) == N for cw in base_cw)
+            t.field = env.xfield
+            t.matrix = [[env.xfield.lift(v) for v in base[r]] + ext[r] for r in range(h)]
+            ext_cw = glue.table_lde(t, dom, draw, xfield=env.xfield)
+            lazy_ext = [cw for cw in ext_cw if type(cw) is DeviceCodeword]  # constant columns stay host lists
+            assert all(cw.kind == "x" for cw in lazy_ext)
+            seen += len(lazy_ext)
+            # the transposition of prove() and the lifted views of Table.extend, before anything is materialised
+            rows = glue.rows_of(base_cw + ext_cw)
+            assert type(rows) is LazyRows and len(rows) == N
+            lifted = glue.lift_codewords(env.xfield, base_cw)
+            assert all(type(cw) is DeviceCodeword and cw.kind == "l" for cw in lifted)
+            r5 = rows[5]
+            assert rows[5] is r5 and rows[-N + 5] is r5 and type(r5) is tuple and len(r5) == fw
+            assert all(r5[k] is (base_cw + ext_cw)[k][5] for k in range(fw))
+            assert vals(r5[:bw]) == [cw[5] for cw in c["base_codewords"]]
+            assert triples(r5[bw:]) == [cw[5] for cw in c["ext_codewords"]]
+            l5 = lifted[0][5]
+            want = env.xfield.lift(base_cw[0][5])
+            assert lifted[0][5] is l5 and pickle.dumps(l5) == pickle.dumps(want)
+            assert (l5.polynomial.coefficients[0] is base_cw[0][5]) if base_cw[0][5].value else l5.polynomial.coefficients == []
+            assert rows[2:4] == [rows[2], rows[3]] and base_cw[0][1:3] == [base_cw[0][1], base_cw[0][2]]
+            with pytest.raises(IndexError):
+                rows[N]
+            with pytest.raises(IndexError):
+                base_cw[0][N]
+            # salted tree over the lazy rows == tree over the same rows as host tuples (same salts)
+            if env.salted_merkle is not None and N & (N - 1) == 0:
+                sm = env.salted_merkle
+                old = sm.urandom
+                try:
+                    sm.urandom = seeded_urandom(77)
+                    lazy_tree = sm.SaltedMerkle(rows)
+                    assert type(lazy_tree.leafs) is LazyLeafs and len(lazy_tree.leafs) == N
+                    leaf3 = lazy_tree.leafs[3]
+                    assert lazy_tree.leafs[3] is leaf3 and leaf3[0] is rows[3]
+                    salt, path = lazy_tree.open(3)
+                    assert salt is leaf3[1] and sm.SaltedMerkle.verify(lazy_tree.root(), 3, salt, path, leaf3[0])
+                    sm.urandom = seeded_urandom(77)
+                    host_tree = sm.SaltedMerkle([tuple(r) for r in rows])
+                    assert host_tree.root() == lazy_tree.root()
+                    assert [s_ for _, s_ in host_tree.leafs] == lazy_tree.leafs.salts
+                    assert host_tree.open(N - 1) == lazy_tree.open(N - 1)
+                finally:
+                    sm.urandom = old
+            # whole codewords through the views: the reference's values and pickles
+            assert [vals(cw) for cw in base_cw] == c["base_codewords"]
+            assert hashlib.sha256(pickle.dumps([list(cw) for cw in base_cw])).hexdigest() == c["base_pickle_sha256"]
+            assert [triples(cw) for cw in ext_cw] == c["ext_codewords"]
+            assert hashlib.sha256(pickle.dumps([list(cw) for cw in ext_cw])).hexdigest() == c["ext_pickle_sha256"]
+            assert list(rows)[5] is r5 and list(lifted[0])[5] is l5 and len(list(rows)) == N
+            # a randomizer-style codeword (code/brainfuck_stark.py:164-167) and its use as transform input
+            poly = env.Polynomial(rand_xfe_list(env, 3, N // 4))
+            rc = dom.xevaluate(poly) if hasattr(dom, "xevaluate") else glue.domain_xevaluate(dom, poly)
+            assert type(rc) is DeviceCodeword and rc.kind == "x"
+            back = glue.domain_xinterpolate(dom, rc)
+            assert triples(back.coefficients[:N // 4]) == triples(poly.coefficients)
+        # outside the scope everything is a plain list again
+        assert type(glue.domain_xevaluate(dom, poly)) is list
+    assert seen > 0
+
+
 def case_quotients_glue(env, glue):
     """SURVEY 8(f) row 1 through the glue (object lists in, codewords out) against the reference's quotient
     codewords (tests/golden/quotients.json): plain lists outside keep_planes(), lazy device codewords and the

@@ -4,6 +4,9 @@ over a host-memory test backend, then (a) every front-end case must reproduce th
 import importlib
 import sys
 
+import numpy as np
+import pickle
+
 import pytest
 
 import frontend_cases as fc
@@ -319,6 +322,49 @@ def test_prove_is_recompiled_with_guarded_combination_block(env, monkeypatch):
             pass
     with pytest.raises(LookupError):
         dropin.guarded_prove_source(Moved.prove)
+
+
+def test_lazy_codewords_inside_prove(env):
+    """the device views prove() works on under the drop-in: rows hook compiled into prove(), every Table.extend wrapped
+    so that its lifting statement runs over the views, and the views themselves against the reference's codewords"""
+    import brainfuck_stark
+    import io_table
+    import instruction_table
+    import memory_table
+    import processor_table
+    from stark_brainfuck_b200 import dropin
+    from stark_brainfuck_b200.glue import DeviceCodeword
+    prove = brainfuck_stark.BrainfuckStark.prove.__wrapped__
+    assert dropin._ROWS_HOOK in prove.__code__.co_names
+    assert all(dropin.lazy_rows_source(stmt) == stmt.split(" = ")[0] + " = %s(%s)" % (dropin._ROWS_HOOK, stmt[stmt.index("*") + 1:-2])
+               for stmt in dropin._ROWS_STATEMENTS)
+    assert brainfuck_stark.__dict__[dropin._ROWS_HOOK]([[1, 2], [3, 4]]) == [(1, 3), (2, 4)]  # host lists: zip as written
+    for cls, meth in ((processor_table.ProcessorTable, "extend"), (instruction_table.InstructionTable, "extend"),
+                      (memory_table.MemoryTable, "extend"), (io_table.IOTable, "extend_iotable")):
+        assert hasattr(cls.__dict__[meth], "__wrapped__"), (cls, meth)
+    fc.case_lazy_codewords(env, env.glue)
+    # Table.extend over device views: the reference's statement sees an empty list, the views are lifted by the glue;
+    # over host lists (outside prove) the method is the reference's own
+    glue = env.glue
+    t = io_table.InputTable(env.field, 2, env.field(7), 8)
+    t.matrix = [[env.field(3)], [env.field(4)]]
+    t.pad()
+    plain = [[env.field(5), env.field(0)]]
+    t.codewords = plain
+    t.extend([env.xfield.one()] * 11, [])
+    assert t.codewords is not plain and t.codewords[0][0].polynomial.coefficients[0] is plain[0][0]
+    assert t.codewords[0][1].polynomial.coefficients == []
+    t2 = io_table.InputTable(env.field, 2, env.field(7), 8)
+    t2.matrix = [[env.field(3)], [env.field(4)]]
+    t2.pad()
+    with glue.keep_planes(lazy=True):
+        view = DeviceCodeword(glue, glue.engine.upload(np.array([[5, 0]], dtype=np.uint64)), env.field, "b")
+        t2.codewords = [view]
+        t2.extend([env.xfield.one()] * 11, [])
+        assert type(t2.codewords[0]) is DeviceCodeword and t2.codewords[0].kind == "l"
+        assert pickle.dumps(list(t2.codewords[0])) == pickle.dumps(t.codewords[0])
+        assert t2.codewords[0][0].polynomial.coefficients[0] is view[0]
+    assert fc.triples([row[-1] for row in t2.matrix]) == fc.triples([row[-1] for row in t.matrix])
 
 
 def test_table_lde_matches_reference(env):

@@ -74,6 +74,10 @@ def test_table_lde(env, mirror_gpu):
     fc.case_lde(env, mirror_gpu.glue())
 
 
+def test_lazy_codewords(env, mirror_gpu):
+    fc.case_lazy_codewords(env, mirror_gpu.glue())
+
+
 def test_quotients_through_the_glue(env, mirror_gpu):
     fc.case_quotients_glue(env, mirror_gpu.glue())
 

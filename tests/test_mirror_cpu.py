@@ -70,6 +70,10 @@ def test_table_lde(env, mirror_cpu):
     fc.case_lde(env, mirror_cpu.glue())
 
 
+def test_lazy_codewords(env, mirror_cpu):
+    fc.case_lazy_codewords(env, mirror_cpu.glue())
+
+
 def test_quotients_through_the_glue(env, mirror_cpu):
     fc.case_quotients_glue(env, mirror_cpu.glue())
 
