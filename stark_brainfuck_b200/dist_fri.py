@@ -91,7 +91,6 @@ class DistCodeword(DeviceCodeword):
         self._layout = layout
         self._local = local_planes  # slot -> (3, blk) device tensor (None on ranks that own nothing)
         self._field = xfield
-        self.kind, self._base = "x", None
         self._n = layout.n
         self._cache = {}
 

@@ -174,6 +174,15 @@ class Glue:
         if kind == "x" and not inverse:
             share = self._shared_output_period(arr, n)
         out = self.engine.ntt(self.engine.upload(arr), _ilog2(n), w, offset=offset, inverse=inverse)
+        if share and lazy and self._lazy and self._kept is not None:
+            # the same identity graph as below, built element by element on first access
+            if share == 1:
+                src = lone_source if lone_source is not None else first
+                assert pow(w, n, P) == 1, "primitive root must be nth root of unity, where n is %d" % n
+                assert n < 2 or pow(w, n // 2, P) != 1, \
+                    "primitive root is not primitive nth root of unity, where n is %d" % n
+                return DeviceCodeword(self, out, src.field, "x", share=1, reps={0: src})
+            return DeviceCodeword(self, out, res_field, "x", share=share)
         if share == 1:
             values = self._lone_coefficient_ntt(lone_source if lone_source is not None else first, w, n)
         elif share:
@@ -1061,8 +1070,10 @@ class DeviceCodeword:
               base codewords): element i wraps base[i] ITSELF as its only coefficient (none when it is zero,
               code/extension_field.py:6-9, :113-116); planes = the base codeword's"""
 
-    def __init__(self, glue, planes, field, kind="x", base=None):
-        assert planes.shape[0] == (3 if kind == "x" else 1)
+    kind, _base, _share, _reps = "x", None, 0, None  # defaults for subclasses with their own constructor (dist_fri)
+
+    def __init__(self, glue, planes, field, kind="x", base=None, share=0, reps=None):
+        assert planes.shape[0] == (3 if kind == "x" else 1) and (not share or kind == "x")
         self._glue = glue
         self._planes = planes
         self._field = field
@@ -1070,6 +1081,11 @@ class DeviceCodeword:
         self._base = base
         self._n = planes.shape[1]
         self._cache = {}
+        # share > 0 (kind "x"): the identity graph of the reference's recursive ntt on a sparse input
+        # (Glue._shared_output_period): element i is a distinct object wrapping the coefficient objects of
+        # representative i % share; share == 1 with reps = {0: the input's lone coefficient element}
+        self._share = share
+        self._reps = {} if reps is None else reps
 
     def __len__(self):
         return self._n
@@ -1086,7 +1102,14 @@ class DeviceCodeword:
     def fill(self, need, vals):
         """vals: (len(need), number of planes) uint64 as gathered from the planes"""
         B = self._glue.B
-        if self.kind == "x":
+        if self._share:
+            mk, xf, X, reps, share = B.make_xfe, self._field, B.ExtensionFieldElement, self._reps, self._share
+            for i, v in zip(need, vals.tolist()):
+                rep = reps.get(i % share)
+                if rep is None:  # outputs i and i % share are equal: either's values build the representative
+                    rep = reps[i % share] = mk(v[0], v[1], v[2], xf)
+                self._cache[i] = X(rep.polynomial, xf)
+        elif self.kind == "x":
             mk, xf = B.make_xfe, self._field
             for i, v in zip(need, vals.tolist()):
                 self._cache[i] = mk(v[0], v[1], v[2], xf)
@@ -1137,6 +1160,17 @@ class DeviceCodeword:
                     for i in range(self._n):
                         if i not in self._cache:
                             self._cache[i] = self._lift(base[i])
+                elif self._share:
+                    todo = [j for j in range(self._share) if j not in self._reps]
+                    if todo:
+                        a = self._glue.engine.download(self._planes)[:, :self._share]
+                        fresh = B.np_to_xfe(a, self._field)
+                        for j in todo:
+                            self._reps[j] = fresh[j]
+                    X, xf, reps, share = B.ExtensionFieldElement, self._field, self._reps, self._share
+                    for i in range(self._n):
+                        if i not in self._cache:
+                            self._cache[i] = X(reps[i % share].polynomial, xf)
                 else:
                     a = self._glue.engine.download(self._planes)
                     fresh = B.np_to_xfe(a, self._field) if self.kind == "x" else B.np_to_bfe(a[0], self._field)

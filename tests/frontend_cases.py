@@ -406,7 +406,7 @@ def case_lazy_codewords(env, glue):
     g = golden("lde.json")
     N = g["N"]
     dom = env.Fri.Domain(env.field(g["offset"]), env.field(g["omega"]), N)
-    seen = 0
+    seen = shared = 0
     for c in g["cases"]:
         h, bw, fw = c["height"], c["base_width"], c["full_width"]
         if not h:
@@ -423,9 +423,9 @@ def case_lazy_codewords(env, glue):
             t.field = env.xfield
             t.matrix = [[env.xfield.lift(v) for v in base[r]] + ext[r] for r in range(h)]
             ext_cw = glue.table_lde(t, dom, draw, xfield=env.xfield)
-            lazy_ext = [cw for cw in ext_cw if type(cw) is DeviceCodeword]  # constant columns stay host lists
-            assert all(cw.kind == "x" for cw in lazy_ext)
-            seen += len(lazy_ext)
+            assert all(type(cw) is DeviceCodeword and cw.kind == "x" for cw in ext_cw)
+            seen += len(ext_cw)
+            shared += sum(1 for cw in ext_cw if cw._share)  # constant columns: outputs share coefficient objects
             # the transposition of prove() and the lifted views of Table.extend, before anything is materialised
             rows = glue.rows_of(base_cw + ext_cw)
             assert type(rows) is LazyRows and len(rows) == N
@@ -472,13 +472,13 @@ def case_lazy_codewords(env, glue):
             assert list(rows)[5] is r5 and list(lifted[0])[5] is l5 and len(list(rows)) == N
             # a randomizer-style codeword (code/brainfuck_stark.py:164-167) and its use as transform input
             poly = env.Polynomial(rand_xfe_list(env, 3, N // 4))
-            rc = dom.xevaluate(poly) if hasattr(dom, "xevaluate") else glue.domain_xevaluate(dom, poly)
+            rc = glue.domain_xevaluate(dom, poly)
             assert type(rc) is DeviceCodeword and rc.kind == "x"
             back = glue.domain_xinterpolate(dom, rc)
             assert triples(back.coefficients[:N // 4]) == triples(poly.coefficients)
         # outside the scope everything is a plain list again
         assert type(glue.domain_xevaluate(dom, poly)) is list
-    assert seen > 0
+    assert seen > 0 and shared > 0
 
 
 def case_quotients_glue(env, glue):

@@ -345,7 +345,7 @@ def test_lazy_codewords_inside_prove(env):
     fc.case_lazy_codewords(env, env.glue)
     # Table.extend over device views: the reference's statement sees an empty list, the views are lifted by the glue;
     # over host lists (outside prove) the method is the reference's own
-    glue = env.glue
+    glue = dropin.current_glue()  # the instance the wrappers consult (another test may have re-installed)
     t = io_table.InputTable(env.field, 2, env.field(7), 8)
     t.matrix = [[env.field(3)], [env.field(4)]]
     t.pad()
