@@ -62,7 +62,9 @@ typedef struct b2s_leaf_templates {
 int b2s_version(void);
 const char *b2s_last_error(void);
 /* Select the CUDA device for the calling thread and create the per-device caches.
- * Fails (B2S_ERR_CUDA) when no sm_100 device is visible: there is no CPU fallback. */
+ * Fails (B2S_ERR_CUDA) when no sm_100 device is visible: there is no CPU fallback.
+ * Scratch memory comes from the device's stream-ordered pool, which keeps up to 2 GiB of freed scratch
+ * (environment B2S_POOL_THRESHOLD_MB overrides the bound; b2s_trim() returns everything to the driver). */
 int b2s_init(int device);
 int b2s_shutdown(void);
 /* Return cached device memory to the driver: the stream-ordered scratch pool (which otherwise keeps up to 2 GiB

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 std::atomic<uint64_t> g_launches{0};
@@ -51,6 +53,7 @@ extern "C" int b2s_init(int device) {
     cudaMemPool_t pool;
     B2S_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thresh = (uint64_t)2 << 30;
+    if (const char *mb = getenv("B2S_POOL_THRESHOLD_MB")) thresh = (uint64_t)strtoull(mb, nullptr, 10) << 20;
     B2S_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     return 0;
 }
