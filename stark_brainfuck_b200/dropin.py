@@ -17,6 +17,12 @@ time lives in every importing module's globals.  install() therefore
      at install time from the reference's own source with that one block guarded by a call into
      the glue (the block itself stays as the fallback) -- the in-memory equivalent of the hunk
      shown in INTEGRATION.md.
+  5. inside prove() the codewords are device views (glue.DeviceCodeword) whose elements are built on first access:
+     Table.lde / ldex / Domain.xevaluate return them, the `list(zip(*codewords))` statements of prove()
+     (code/brainfuck_stark.py:178, :196) go through a hook compiled into the same recompiled prove(), and the four
+     Table.extend methods are wrapped so that their last statement (`self.codewords = [[xfield.lift(c) ...`, e.g.
+     code/io_table.py:106-107) runs over an empty list while the glue lifts the views.  A proof opens a few hundred
+     rows of its 46 codewords; building every element object was most of its host time.
 uninstall() restores every original (needed to time the CPU reference in the same process).
 """
 import importlib
