@@ -7,7 +7,6 @@ import hashlib
 import os
 import sys
 
-import numpy as np
 import pytest
 
 from util import golden, have_golden, rand_xfe, root_of_unity

@@ -2,7 +2,6 @@
 over a host-memory test backend, then (a) every front-end case must reproduce the golden values,
 (b) the reference's own test files run unchanged, (c) uninstall() restores the originals."""
 import importlib
-import sys
 
 import numpy as np
 import pickle

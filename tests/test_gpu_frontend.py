@@ -1,7 +1,5 @@
 """GPU parity, object level: the reference-named front end (standalone mirror) over libb2s.so
 against golden values and byte-exact transcripts produced by the unmodified reference."""
-import hashlib
-import json
 import os
 
 import pytest
