@@ -24,8 +24,13 @@ PROGRAMS = {
     "pppp": ("++++", ""),
     "io": ("++[>,.<-]", "ab"),
     "hello": ("++++++++[>++++[>++>+++>+++>+<<<<-]>+>+>->>+[<]<-]>>.>---.+++++++..+++.>>.<-.<.+++.------.--------.>>+.>++.", ""),
+    # 8 780 cycles, trace padded to 2^14 rows, FRI domain 2^20 = BASELINE config 5's size
+    "big": ("+++++++++++[>+++++++++++[>+++++++++++[>+<-]<-]<-]", ""),
 }
-EXPECTED = {"hello": "540a9a28053b3195231dc7736163b760d8015a7159b973b85307e45ace4a6f3e"}
+# hello: the hash of tests/test_e2e_prove.py; big: the proof the GPU produced with the reference staged next to it
+# (profiles/artifacts/r02s_prove_2p20_domain_b200.json), reproduced here by the CPU oracle
+EXPECTED = {"hello": "540a9a28053b3195231dc7736163b760d8015a7159b973b85307e45ace4a6f3e",
+            "big": "a9ce6dd2406c1439d34c285d4396f8a07aa3c43400c019c2bb2a28e2f4a5ecc9"}
 
 
 def main(name):

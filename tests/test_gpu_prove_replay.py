@@ -18,7 +18,10 @@ from util import GOLDEN  # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name,domain,min_calls", [("pppp", 1024, 70), ("io", 2048, 70), ("hello", 1 << 17, 80)])
+# "big": an 8 780-cycle program on a 2^20 FRI domain, BASELINE config 5's size (proof a9ce6dd2..., the same bytes the GPU
+# produced with the reference staged next to it and the CPU oracle produced when the trace was recorded)
+@pytest.mark.parametrize("name,domain,min_calls", [("pppp", 1024, 70), ("io", 2048, 70), ("hello", 1 << 17, 80),
+                                                   ("big", 1 << 20, 80)])
 def test_prove_command_stream_replays_bit_exact(name, domain, min_calls):
     from stark_brainfuck_b200 import Engine
     path = os.path.join(GOLDEN, "trace_%s.bin" % name)
