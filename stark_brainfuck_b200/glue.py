@@ -228,6 +228,20 @@ class Glue:
         X = self.B.ExtensionFieldElement
         return [X(source.polynomial, source.field) for _ in range(n)]
 
+    def _zeros_ntt(self, primitive_root, zero, n, lazy):
+        """ntt(primitive_root, [zero] * n): the codeword of an EMPTY polynomial (the input / output tables of a program
+        without input / output, code/table.py:117-118 -> code/fri.py:26-37).  The reference's recursion returns n
+        distinct zero elements; inside prove() they are a device view over a zero plane (the transform still runs:
+        the library checks the root's order like code/ntt.py:13-16)."""
+        w = self.base_value(primitive_root, "primitive_root")
+        B = self.B
+        if not (lazy and self._lazy and self._kept is not None) or n < 2 or n & (n - 1) or w is None or \
+                not ((B.is_xfe(zero) and zero.is_zero()) or (B.is_bfe(zero) and zero.value == 0)):
+            return self.ntt(primitive_root, [zero] * n)
+        kind = "x" if B.is_xfe(zero) else "b"
+        out = self.engine.ntt(self.engine.zeros(3 if kind == "x" else 1, n), _ilog2(n), w)
+        return DeviceCodeword(self, out, zero.field, kind)
+
     def ntt(self, primitive_root, values):
         """code/ntt.py:4-23"""
         assert len(values) & (len(values) - 1) == 0, "cannot compute ntt of non-power-of-two sequence"
@@ -253,7 +267,7 @@ class Glue:
         if m == 0:
             # nothing tells us the element class; the reference pads with offset.field.zero()
             zero = offset.field.zero()
-            return self.ntt(generator, [zero] * order) if order > 1 else [zero] * order
+            return self._zeros_ntt(generator, zero, order, lazy) if order > 1 else [zero] * order
         assert order & (order - 1) == 0, "cannot compute ntt of non-power-of-two sequence"
         assert m <= order, "polynomial has more coefficients than the domain has points"
         off = self.base_value(offset, "offset")
@@ -382,7 +396,7 @@ class Glue:
         n = dom.length
         if not coeffs:
             zero = dom.omega.field.zero()
-            return self.ntt(dom.omega, [zero] * n)
+            return self._zeros_ntt(dom.omega, zero, n, True)
         assert len(coeffs) <= n, "polynomial has more coefficients than the domain has points"
         if n <= 1:
             return self.B.Polynomial(coeffs).scale(dom.offset).coefficients
