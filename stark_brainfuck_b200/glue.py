@@ -883,7 +883,7 @@ class Glue:
             return None
         salt0 = salts[0]
         frame = marshal.salt_frame(salt0) if type(salt0) is bytes else None
-        if frame is None or any(type(x) is not bytes or len(x) != len(salt0) for x in salts):
+        if frame is None or set(map(type, salts)) != {bytes} or set(map(len, salts)) != {len(salt0)}:
             return None
         tpl = marshal.row_template(self.B, rows[0])
         if tpl is None:
