@@ -171,6 +171,43 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
         return x
     set_attr(binding.ExtensionField, "lift", lift)
 
+    # ExtensionField.sample / BaseField.sample (code/extension_field.py:100-111, code/algebra.py:138-142; SURVEY 8(a)
+    # a1 / a3): the prover draws its randomizer polynomial with max_degree + 1 = N/4 calls (code/brainfuck_stark.py:
+    # 164-165), each a Python loop over the bytes, three constructors and two Polynomial.degree() scans.  Same
+    # values ((acc << 8) ^ b over the bytes is the big-endian integer), same object graph, built directly.
+    Bf, Bcls = binding.BaseField, binding.BaseFieldElement
+    orig_bsample, orig_xsample = Bf.sample, binding.ExtensionField.sample
+
+    def bsample(self, byte_array):
+        if type(byte_array) is not bytes:
+            return orig_bsample(self, byte_array)
+        o = Bcls.__new__(Bcls)
+        o.__dict__ = {"value": int.from_bytes(byte_array, "big") % self.p, "field": self}
+        return o
+
+    def xsample(self, byte_array):
+        if type(byte_array) is not bytes:
+            return orig_xsample(self, byte_array)
+        parts = self.modulus.degree()
+        width = len(byte_array) // parts
+        inner = self.modulus.coefficients[0].field
+        p = inner.p
+        vals = [int.from_bytes(byte_array[k * width:(k + 1) * width], "big") % p for k in range(parts)]
+        while vals and vals[-1] == 0:  # ExtensionFieldElement.__init__ trims (code/extension_field.py:6-9)
+            vals.pop()
+        co = []
+        for v in vals:
+            o = Bcls.__new__(Bcls)
+            o.__dict__ = {"value": v, "field": inner}
+            co.append(o)
+        q = Pn.__new__(Pn)
+        q.__dict__ = {"coefficients": co}
+        x = X.__new__(X)
+        x.__dict__ = {"polynomial": q, "field": self}
+        return x
+    set_attr(Bf, "sample", bsample)
+    set_attr(binding.ExtensionField, "sample", xsample)
+
     # -- 4. next row: quotient codewords of the AIR ---------------------------
     # DEBUG keeps the reference's own loops (they print and assert degree bounds on the way).
     if quotients:

@@ -323,6 +323,40 @@ def test_prove_is_recompiled_with_guarded_combination_block(env, monkeypatch):
         dropin.guarded_prove_source(Moved.prove)
 
 
+def test_sample_and_lift_build_the_reference_object_graph(env):
+    """the constructor-free ExtensionField.sample / lift and BaseField.sample of the drop-in against the reference's
+    own methods: same pickles (values, trimming, field objects) for bytes of every length the prover uses"""
+    import random
+    import algebra
+    import extension_field
+    from stark_brainfuck_b200 import dropin
+    R = random.Random(12)
+    bsample = algebra.BaseField.sample.__wrapped__ if hasattr(algebra.BaseField.sample, "__wrapped__") else None
+    saved = dropin._state["saved"]["attrs"]
+    orig = {(obj.__name__, name): fn for obj, name, fn in saved if name in ("sample", "lift")}
+    ob, ox, ol = orig[("BaseField", "sample")], orig[("ExtensionField", "sample")], orig[("ExtensionField", "lift")]
+    assert bsample is None and ob is not algebra.BaseField.sample and ox is not extension_field.ExtensionField.sample
+    f, xf = env.field, env.xfield
+    cases = [b"", b"\x00", b"\x01\x02", bytes(24), bytes(27), b"\xff" * 24, b"\xff" * 27, bytes(16) + b"\x07" * 8,
+             bytes(8) + b"\x01" + bytes(15), b"\x05" + bytes(23)]
+    cases += [bytes(R.getrandbits(8) for _ in range(n)) for n in (1, 2, 3, 7, 24, 24, 27, 27, 32, 32, 64, 100)]
+    P = f.p
+    cases += [(P).to_bytes(8, "big") * 3, (P - 1).to_bytes(8, "big") * 3, (P + 5).to_bytes(9, "big") * 3]
+    for b in cases:
+        assert pickle.dumps(f.sample(b)) == pickle.dumps(ob(f, b)), b
+        got, want = xf.sample(b), ox(xf, b)
+        assert pickle.dumps(got) == pickle.dumps(want), b
+        assert got.field is xf and all(c.field is xf.modulus.coefficients[0].field for c in got.polynomial.coefficients)
+        assert pickle.dumps([got, got]) == pickle.dumps([want, want])
+    for b in (list(b"\x01\x02\x03"), bytearray(b"\x09" * 24)):  # other byte containers: the reference's own code path
+        assert pickle.dumps(xf.sample(b)) == pickle.dumps(ox(xf, b)) and f.sample(b).value == ob(f, b).value
+    for v in (0, 1, P - 1):
+        e = env.BaseFieldElement(v, f)
+        assert pickle.dumps(xf.lift(e)) == pickle.dumps(ol(xf, e)) and xf.lift(xf.lift(e)) is not None
+    x = xf.sample(b"\x01" * 27)
+    assert xf.lift(x) is x
+
+
 def test_lazy_codewords_inside_prove(env):
     """the device views prove() works on under the drop-in: rows hook compiled into prove(), every Table.extend wrapped
     so that its lifting statement runs over the views, and the views themselves against the reference's codewords"""
