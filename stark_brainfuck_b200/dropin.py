@@ -208,6 +208,24 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
     set_attr(Bf, "sample", bsample)
     set_attr(binding.ExtensionField, "sample", xsample)
 
+    # Polynomial.degree (code/univariate.py:8-18): the index of the last non-zero coefficient, found by building a
+    # zero element, a list of n copies of it, comparing the lists element by element and then scanning all n
+    # coefficients -- and every ExtensionFieldElement constructor calls it (code/extension_field.py:7-8): 2.7 M calls
+    # in a proof on a 2^20 domain, a third of its host time.  Same integer, found from the top; coefficients that are
+    # not base-field elements (no `.value`) take the reference's own path.
+    orig_degree = Polynomial.degree
+
+    def degree(self):
+        co = self.coefficients
+        try:
+            for i in range(len(co) - 1, -1, -1):
+                if co[i].value != 0:
+                    return i
+        except AttributeError:
+            return orig_degree(self)
+        return -1
+    set_attr(Polynomial, "degree", degree)
+
     # -- 4. next row: quotient codewords of the AIR ---------------------------
     # DEBUG keeps the reference's own loops (they print and assert degree bounds on the way).
     if quotients:

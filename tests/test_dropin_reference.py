@@ -355,6 +355,18 @@ def test_sample_and_lift_build_the_reference_object_graph(env):
         assert pickle.dumps(xf.lift(e)) == pickle.dumps(ol(xf, e)) and xf.lift(xf.lift(e)) is not None
     x = xf.sample(b"\x01" * 27)
     assert xf.lift(x) is x
+    # Polynomial.degree: the same integer as the reference's scan, for base-field and extension-field coefficients
+    import univariate
+    od = [fn for obj, name, fn in saved if name == "degree"][0]
+    assert od is not univariate.Polynomial.degree
+    for _ in range(300):
+        n = R.randrange(0, 9)
+        vals = [R.choice([0, 0, 1, P - 1, R.randrange(P)]) for _ in range(n)]
+        pb = univariate.Polynomial([env.BaseFieldElement(v, f) for v in vals])
+        assert pb.degree() == od(pb), vals
+        px = univariate.Polynomial([fc.X(env, v, 0, R.choice([0, v])) for v in vals])
+        assert px.degree() == od(px), vals
+    assert univariate.Polynomial([]).degree() == -1
 
 
 def test_lazy_codewords_inside_prove(env):
