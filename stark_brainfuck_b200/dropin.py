@@ -208,6 +208,141 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
     set_attr(Bf, "sample", bsample)
     set_attr(binding.ExtensionField, "sample", xsample)
 
+    # ExtensionField.multiply / add / subtract / negate (code/extension_field.py:65-75).  The reference
+    # multiplies two elements through a schoolbook Polynomial product and a long division by the modulus, dozens of
+    # temporary objects and degree() scans per call (85 us; every Table.extend is made of these: 190 000 products in a
+    # proof on a 2^20 domain).  Same values AND the same object graph, which pickle sees when a result (a terminal)
+    # goes into the proof stream -- derived from code/univariate.py:23-51, :90-111:
+    #   product   all coefficients are new elements of left.coefficients[0].field; when the product needs no reduction
+    #             (degree < 3) the positions no non-zero left coefficient reached hold ONE shared zero element
+    #   sum       an empty operand returns the other one's coefficient OBJECTS (for a difference: their new negations,
+    #             each in its own field); otherwise new elements of left.coefficients[0].field
+    # Anything unusual (more than three coefficients, untrimmed operands, another modulus or field) takes the
+    # reference's own path.
+    XF = binding.ExtensionField
+    orig_mul, orig_add, orig_sub, orig_neg = XF.multiply, XF.add, XF.subtract, XF.negate
+    standard = {}
+
+    def is_standard(xf):
+        hit = standard.get(id(xf))
+        if hit is None or hit[0] is not xf:
+            try:
+                m = xf.modulus.coefficients
+                q = m[0].field.p
+                ok = [c.value for c in m] == [1, q - 1, 0, 1] and all(c.field.p == q for c in m)
+            except (AttributeError, IndexError):
+                ok, q = False, None
+            hit = standard[id(xf)] = (xf, ok, q)
+        return hit[1], hit[2]
+
+    def operands(xf, left, right):
+        """(coefficient lists, their values, p) when both are trimmed elements of at most three coefficients over
+        base fields of the modulus' characteristic; None otherwise"""
+        ok, q = is_standard(xf)
+        if not ok or type(left) is not X or type(right) is not X:
+            return None
+        L, R = left.polynomial.coefficients, right.polynomial.coefficients
+        if len(L) > 3 or len(R) > 3:
+            return None
+        try:
+            lv, rv = [c.value for c in L], [c.value for c in R]
+            if any(c.field.p != q for c in L) or any(c.field.p != q for c in R):
+                return None
+        except AttributeError:
+            return None
+        if (lv and not 0 < lv[-1] < q) or (rv and not 0 < rv[-1] < q):
+            return None
+        return L, R, lv, rv, q
+
+    def element(xf, co):
+        poly = Pn.__new__(Pn)
+        poly.__dict__ = {"coefficients": co}
+        x = X.__new__(X)
+        x.__dict__ = {"polynomial": poly, "field": xf}
+        return x
+
+    def mk(v, f):
+        o = Bcls.__new__(Bcls)
+        o.__dict__ = {"value": v, "field": f}
+        return o
+
+    def xmul(self, left, right):
+        ops = operands(self, left, right)
+        if ops is None:
+            return orig_mul(self, left, right)
+        L, R, lv, rv, q = ops
+        a, b = len(lv), len(rv)
+        if a == 0 or b == 0:
+            return element(self, [])
+        n = a + b - 1
+        c, touched = [0] * n, [False] * n
+        for i, x in enumerate(lv):
+            if x == 0:
+                continue  # code/univariate.py:46-47
+            for j, y in enumerate(rv):
+                c[i + j] += x * y
+                touched[i + j] = True
+        f = L[0].field
+        if n <= 3:  # no reduction: the product polynomial itself is the remainder (code/univariate.py:93-94)
+            zero = None
+            co = []
+            for k in range(n):
+                if touched[k]:
+                    co.append(mk(c[k] % q, f))
+                else:
+                    if zero is None:
+                        zero = mk(0, f)
+                    co.append(zero)
+            return element(self, co)
+        c3, c4 = c[3], (c[4] if n == 5 else 0)  # X^3 = X - 1, X^4 = X^2 - X
+        r = [(c[0] - c3) % q, (c[1] + c3 - c4) % q, (c[2] + c4) % q]
+        while r and r[-1] == 0:
+            r.pop()
+        return element(self, [mk(v, f) for v in r])
+
+    def xadd(self, left, right):
+        ops = operands(self, left, right)
+        if ops is None:
+            return orig_add(self, left, right)
+        L, R, lv, rv, q = ops
+        if not lv:
+            return element(self, list(R))  # code/univariate.py:24-25: the other operand's coefficient objects
+        if not rv:
+            return element(self, list(L))
+        n = max(len(lv), len(rv))
+        r = [((lv[k] if k < len(lv) else 0) + (rv[k] if k < len(rv) else 0)) % q for k in range(n)]
+        while r and r[-1] == 0:
+            r.pop()
+        f = L[0].field
+        return element(self, [mk(v, f) for v in r])
+
+    def xsub(self, left, right):
+        ops = operands(self, left, right)
+        if ops is None:
+            return orig_sub(self, left, right)
+        L, R, lv, rv, q = ops
+        if not lv:
+            return element(self, [mk((q - c.value) % q, c.field) for c in R])  # the negations, each in its own field
+        if not rv:
+            return element(self, list(L))
+        n = max(len(lv), len(rv))
+        r = [((lv[k] if k < len(lv) else 0) - (rv[k] if k < len(rv) else 0)) % q for k in range(n)]
+        while r and r[-1] == 0:
+            r.pop()
+        f = L[0].field
+        return element(self, [mk(v, f) for v in r])
+
+    def xneg(self, operand):
+        ops = operands(self, operand, operand)
+        if ops is None:
+            return orig_neg(self, operand)
+        L, _, lv, _, q = ops
+        return element(self, [mk((q - c.value) % q, c.field) for c in L])
+    set_attr(XF, "multiply", xmul)
+    set_attr(XF, "add", xadd)
+    set_attr(XF, "subtract", xsub)
+    set_attr(XF, "negate", xneg)
+
     # Polynomial.degree (code/univariate.py:8-18): the index of the last non-zero coefficient, found by building a
     # zero element, a list of n copies of it, comparing the lists element by element and then scanning all n
     # coefficients -- and every ExtensionFieldElement constructor calls it (code/extension_field.py:7-8): 2.7 M calls

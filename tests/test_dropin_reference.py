@@ -369,6 +369,64 @@ def test_sample_and_lift_build_the_reference_object_graph(env):
     assert univariate.Polynomial([]).degree() == -1
 
 
+def test_extension_field_arithmetic_builds_the_reference_object_graph(env):
+    """the direct ExtensionField.multiply / add / subtract / negate of the drop-in against the reference's own methods
+    (Polynomial product + long division): pickles of (operands, result) -- values, trimming, the field object of every
+    coefficient, coefficient objects shared with an operand or with each other -- over sparse, empty and full operands
+    whose coefficients carry different BaseField objects"""
+    import random
+    import algebra
+    import extension_field
+    import univariate
+    from stark_brainfuck_b200 import dropin
+    saved = dropin._state["saved"]["attrs"]
+    orig = {name: fn for obj, name, fn in saved if obj is extension_field.ExtensionField}
+    XF = extension_field.ExtensionField
+    assert all(orig[n] is not XF.__dict__[n] for n in ("multiply", "add", "subtract", "negate"))
+    R = random.Random(31)
+    xf = env.xfield
+    P = env.field.p
+    fields = [env.field, xf.modulus.coefficients[0].field, algebra.BaseField.main(), algebra.BaseField.main()]
+
+    def elem(pattern):
+        co = []
+        for k in pattern:
+            v = 0 if k == "0" else (R.choice([1, P - 1, 2]) if k == "s" else R.randrange(1, P))
+            co.append(algebra.BaseFieldElement(v, R.choice(fields)))
+        return extension_field.ExtensionFieldElement(univariate.Polynomial(co), xf)
+    patterns = ["", "r", "s", "0r", "rr", "00r", "0rr", "r0r", "rrr", "sss", "s0s", "00s"]
+    n = 0
+    for pa in patterns:
+        for pb in patterns:
+            for _ in range(3):
+                a, b = elem(pa), elem(pb)
+                for name in ("multiply", "add", "subtract"):
+                    got, want = XF.__dict__[name](xf, a, b), orig[name](xf, a, b)
+                    assert pickle.dumps((a, b, got)) == pickle.dumps((a, b, want)), (name, pa, pb)
+                    assert got.field is xf
+                    n += 1
+                assert pickle.dumps((a, xf.negate(a))) == pickle.dumps((a, orig["negate"](xf, a)))
+                assert pickle.dumps((a, a * a, a - a, a + a)) == pickle.dumps(
+                    (a, orig["multiply"](xf, a, a), orig["subtract"](xf, a, a), orig["add"](xf, a, a)))
+    assert n > 1200
+    # products that cancel to a lower degree, and operands the fast path must hand to the reference: untrimmed
+    # coefficient lists, four coefficients, a foreign modulus
+    one, x = xf.one(), elem("0s")
+    inv = x.inverse()
+    assert pickle.dumps((x, inv, x * inv)) == pickle.dumps((x, inv, orig["multiply"](xf, x, inv)))
+    long = extension_field.ExtensionFieldElement.__new__(extension_field.ExtensionFieldElement)
+    long.__dict__ = {"polynomial": univariate.Polynomial([env.field(1), env.field(2), env.field(3), env.field(4)]), "field": xf}
+    untrimmed = extension_field.ExtensionFieldElement.__new__(extension_field.ExtensionFieldElement)
+    untrimmed.__dict__ = {"polynomial": univariate.Polynomial([env.field(5), env.field(0)]), "field": xf}
+    for odd in (long, untrimmed):
+        for name in ("multiply", "add", "subtract"):
+            assert pickle.dumps(XF.__dict__[name](xf, odd, one)) == pickle.dumps(orig[name](xf, odd, one))
+            assert pickle.dumps(XF.__dict__[name](xf, one, odd)) == pickle.dumps(orig[name](xf, one, odd))
+    other = extension_field.ExtensionField(univariate.Polynomial([env.field(2), env.field(P - 1), env.field(0), env.field(1)]))
+    y, z = other.sample(bytes(range(27))), other.sample(bytes(range(3, 30)))
+    assert pickle.dumps(other.multiply(y, z)) == pickle.dumps(orig["multiply"](other, y, z))
+
+
 def test_lazy_codewords_inside_prove(env):
     """the device views prove() works on under the drop-in: rows hook compiled into prove(), every Table.extend wrapped
     so that its lifting statement runs over the views, and the views themselves against the reference's codewords"""
