@@ -584,8 +584,8 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
             extra["prove_hello_world_device_replay_ms"] = (time.perf_counter() - t0) * 1e3
             extra["prove_hello_world_engine_calls"] = rep["calls"]
-            extra["prove_hello_world_b200_wall_s"] = "1.1 (unmodified prove() with the reference staged next to the GPU: profiles/artifacts/r02bx_hello_world_prove_b200_1.1s.json)"
-            extra["prove_2p20_domain_b200_wall_s"] = "7.9 (8 780-cycle program, unmodified prove(), reference verifier accepts: profiles/artifacts/r02bx_prove_2p20_domain_b200_7.9s.json)"
+            extra["prove_hello_world_b200_wall_s"] = "0.6 (unmodified prove() with the reference staged next to the GPU: profiles/artifacts/r02cb_hello_world_prove_b200_0.6s.json)"
+            extra["prove_2p20_domain_b200_wall_s"] = "4.0 (8 780-cycle program, unmodified prove(), reference verifier accepts: profiles/artifacts/r02cb_prove_2p20_domain_b200_4.0s.json)"
             sys.path.insert(0, os.path.join(ROOT, "profiles", "microbench"))
             import prove_device_pipeline
             extra["prove_2p20_domain_device_pipeline_ms"] = prove_device_pipeline.pipeline_ms(eng, reps=2)["ms"]

@@ -185,14 +185,19 @@ def install(reference_dir=None, engine=None, quotients=True, salted=True, combin
         o.__dict__ = {"value": int.from_bytes(byte_array, "big") % self.p, "field": self}
         return o
 
+    shape = {}  # id(extension field) -> (the field, degree of its modulus, its inner base field, p)
+
     def xsample(self, byte_array):
         if type(byte_array) is not bytes:
             return orig_xsample(self, byte_array)
-        parts = self.modulus.degree()
+        hit = shape.get(id(self))
+        if hit is None or hit[0] is not self or hit[2] is not self.modulus.coefficients[0].field:
+            inner = self.modulus.coefficients[0].field
+            hit = shape[id(self)] = (self, self.modulus.degree(), inner, inner.p)
+        _, parts, inner, p = hit
         width = len(byte_array) // parts
-        inner = self.modulus.coefficients[0].field
-        p = inner.p
-        vals = [int.from_bytes(byte_array[k * width:(k + 1) * width], "big") % p for k in range(parts)]
+        frm = int.from_bytes
+        vals = [frm(byte_array[k * width:(k + 1) * width], "big") % p for k in range(parts)]
         while vals and vals[-1] == 0:  # ExtensionFieldElement.__init__ trims (code/extension_field.py:6-9)
             vals.pop()
         co = []
