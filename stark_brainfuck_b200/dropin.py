@@ -10,7 +10,9 @@ time lives in every importing module's globals.  install() therefore
      fast_multiply & co. pick them up) and in every loaded module whose global IS the original;
   3. patches class attributes, which every importer shares: Polynomial.scale/evaluate_domain,
      Fri.Domain.evaluate/xevaluate/interpolate/xinterpolate, Fri.commit/query/query_last/prove,
-     Merkle.__init__/open, ExtensionField.lift  (Merkle.root/verify and Fri.verify stay the reference's).
+     Merkle.__init__/open (Merkle.root/verify and Fri.verify stay the reference's), and the per-element host
+     arithmetic of SURVEY 8(a) a1 / a3 by direct equivalents with the same values and object graph:
+     ExtensionField.lift/sample/multiply/add/subtract/negate, BaseField.sample, Polynomial.degree.
   4. next rows: Table.*_quotients / PermutationArgument.quotient, SaltedMerkle.__init__, and the
      nonlinear combination.  The combination is INLINE in BrainfuckStark.prove
      (code/brainfuck_stark.py:241-298), so there is no attribute to rebind: prove() is recompiled
