@@ -166,11 +166,12 @@ extern "C" int b2s_quotients(const uint64_t *d_cw, uint64_t N, uint32_t width, u
                              uint64_t offset, uint64_t omega, uint64_t *d_out, int *h_zero_flag,
                              const uint8_t *h_base_columns, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (N == 0 || (N & (N - 1)) || shift >= N || width == 0 || zerofier_kind < 1 || zerofier_kind > 3) {
+    if (N == 0 || (N & (N - 1)) || width == 0 || zerofier_kind < 1 || zerofier_kind > 3) {
         b2s_set_error("quotients: bad arguments (N %llu, width %u, shift %llu, zerofier %u)", (unsigned long long)N, width,
                       (unsigned long long)shift, zerofier_kind);
         return B2S_ERR_ARG;
     }
+    shift &= N - 1;  // rows are taken modulo N: a table of height 1 has unit distance N (code/table.py:37-40)
     if (h_zero_flag) *h_zero_flag = 0;
     if (n_constraints == 0) return 0;
     const u32 n_mono = h_mono_off[n_constraints];

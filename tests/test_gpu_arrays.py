@@ -303,6 +303,12 @@ def test_quotients_golden_and_oracle(eng):
                 ref, rv = orc.quotients(cw, N // 8, *prog, kind, height, oinv, 7, root_of_unity(logn))
                 assert vanishes == rv is False
                 assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), (logn, lifted, kind, height)
+    # rows are taken modulo N: a table of height 1 has unit distance N (code/table.py:37-40), and more wraps around
+    for shift in (N, N + 3, 5 * N + 1):
+        out, vanishes = eng.quotients(d, shift, *prog, 2, 8, oinv, 7, root_of_unity(logn))
+        ref, rv = orc.quotients(cw, shift, *prog, 2, 8, oinv, 7, root_of_unity(logn))
+        assert not vanishes and not rv
+        assert np.array_equal(eng.download(out.reshape(-1, N)).reshape(-1, 3, N), ref), shift
     # offset 1 puts x = 1 on the domain: boundary zerofier vanishes
     name, cw, shift, prog, kind, height, oinv, want = next(iter(quotient_cases(g)))
     W, _, N = cw.shape

@@ -27,7 +27,8 @@ def _prove(tmp_path, *args):
     res = json.load(open(out))
     keep = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(keep):
-        with open(os.path.join(keep, "e2e_prove_gpu_%s.json" % (args[0] if args else "pppp")), "w") as f:
+        tag = (args[2][:-5] if len(args) > 2 else args[0]) if args else "pppp"
+        with open(os.path.join(keep, "e2e_prove_gpu_%s.json" % tag), "w") as f:
             json.dump(res, f, indent=1)
     return res
 
@@ -42,3 +43,18 @@ def test_hello_world_prove_on_the_gpu_is_accepted_by_the_reference_verifier(tmp_
     res = _prove(tmp_path, "hello")
     assert res["reference_verifier_accepts"] is True and res["fri_domain_length"] == 1 << 17
     assert res["proof_sha256"] == "540a9a28053b3195231dc7736163b760d8015a7159b973b85307e45ace4a6f3e"
+
+
+@pytest.mark.parametrize("source,inputs,name,domain", [("++[>,.<-]", "ab", "bfs_io.json", 2048),
+                                                       ("+++++[>,.<-]", "hello", "bfs_echo.json", 4096),
+                                                       ("+++[>+++[>+<-]<-]>>.", "", "bfs_nested.json", 8192),
+                                                       ("++++++++[>++++++++<-]>+.", "", "bfs_A.json", 16384),
+                                                       ("++++++++++[>+++++++>++++++++++<<-]>++.>+.", "", "bfs_He.json",
+                                                        32768)])
+def test_programs_with_loops_and_io_on_the_gpu_are_byte_identical(tmp_path, source, inputs, name, domain):
+    """the five other programs whose all-reference proofs are recorded (tests/golden/bfs_*.json; the reference needs
+    350 ... 6 109 s each): input and output tables of height 0, 1 (unit distance = the whole domain), 2 and more"""
+    res = _prove(tmp_path, source, inputs, name)
+    assert res["reference_verifier_accepts"] is True and res["byte_identical_to_reference_proof"] is True
+    assert res["fri_domain_length"] == domain
+
