@@ -763,6 +763,10 @@ if __name__ == "__main__":
             group_bfs("++++++++++[>+++++++>++++++++++<<-]>++.>+.", (), "bfs_He.json")
         elif grp == "bfs_echo":
             group_bfs("+++++[>,.<-]", tuple("hello"), "bfs_echo.json")
+        elif grp == "bfs_cat":  # one input, one output symbol: both IO tables of height 1 (unit distance = the domain)
+            group_bfs(",.", ("x",), "bfs_cat.json")
+        elif grp == "bfs_two":  # two output symbols, then one input symbol
+            group_bfs("++..,", ("q",), "bfs_two.json")
         elif grp == "air":
             group_air()
         elif grp == "lde":

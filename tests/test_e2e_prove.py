@@ -41,7 +41,9 @@ def test_hello_world_prove_is_accepted_by_the_reference_verifier(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference checkout not available")
-@pytest.mark.parametrize("source,inputs,name,domain", [("++[>,.<-]", "ab", "bfs_io.json", 2048),
+@pytest.mark.parametrize("source,inputs,name,domain", [(",.", "x", "bfs_cat.json", 512),
+                                                       ("++..,", "q", "bfs_two.json", 1024),
+                                                       ("++[>,.<-]", "ab", "bfs_io.json", 2048),
                                                        ("+++++[>,.<-]", "hello", "bfs_echo.json", 4096),
                                                        ("+++[>+++[>+<-]<-]>>.", "", "bfs_nested.json", 8192),
                                                        ("++++++++[>++++++++<-]>+.", "", "bfs_A.json", 16384),

@@ -45,7 +45,9 @@ def test_hello_world_prove_on_the_gpu_is_accepted_by_the_reference_verifier(tmp_
     assert res["proof_sha256"] == "540a9a28053b3195231dc7736163b760d8015a7159b973b85307e45ace4a6f3e"
 
 
-@pytest.mark.parametrize("source,inputs,name,domain", [("++[>,.<-]", "ab", "bfs_io.json", 2048),
+@pytest.mark.parametrize("source,inputs,name,domain", [(",.", "x", "bfs_cat.json", 512),
+                                                       ("++..,", "q", "bfs_two.json", 1024),
+                                                       ("++[>,.<-]", "ab", "bfs_io.json", 2048),
                                                        ("+++++[>,.<-]", "hello", "bfs_echo.json", 4096),
                                                        ("+++[>+++[>+<-]<-]>>.", "", "bfs_nested.json", 8192),
                                                        ("++++++++[>++++++++<-]>+.", "", "bfs_A.json", 16384),
