@@ -3,7 +3,7 @@
 libb2s.so on cuda:0 and once over the host-memory test backend (CPU oracle), same seeded urandom: the two proofs must be
 byte-identical and the reference's verifier must accept.  Needs the staged reference (baseline/_ref/code) and a GPU.
 
-    python profiles/microbench/fuzz_prove_gpu.py [n_programs] [seed]      -> gpurun_out/fuzz_prove_gpu.json
+    python profiles/microbench/fuzz_prove_gpu.py [n_programs] [seed] [nested]      -> gpurun_out/fuzz_prove_gpu.json
 """
 import json
 import os
@@ -49,6 +49,14 @@ def program(R):
     return src, "".join(chr(R.randrange(1, 120)) for _ in range(n_in))
 
 
+def nested_program(R):
+    """two nested counted loops around a small body: hundreds to a few thousand cycles (FRI domains 2^14 ... 2^18)"""
+    a, b = R.randrange(3, 12), R.randrange(3, 12)
+    body = "".join(R.choice(["+", "+.", ">+<", "-", "++"]) for _ in range(R.randrange(1, 4)))
+    tail = R.choice(["", ".", ">.<", ",."])
+    return "+" * a + "[>" + "+" * b + "[>" + body + "<-]<-]" + tail, "z" if "," in tail else ""
+
+
 def run(backend, source, inputs):
     with tempfile.TemporaryDirectory() as tmp:
         out = os.path.join(tmp, "r.json")
@@ -79,8 +87,9 @@ def main():
     R = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 7)
     rows, bad = [], 0
     k = 0
+    make = nested_program if len(sys.argv) > 3 and sys.argv[3] == "nested" else program
     while k < n:
-        src, inp = program(R)
+        src, inp = make(R)
         inp = consumed_inputs(src, inp)
         if inp is None:
             continue
